@@ -1,0 +1,107 @@
+/*
+ * mscnn_b200 -- C ABI of the B200-native MS-CNN detection forward path.
+ *
+ * The reference (zhaoweicai/mscnn, a Caffe fork) has no C ABI: its boundary for this path is
+ * the C++ class caffe::Layer<Dtype> (include/caffe/layer.hpp:33-445) whose Forward_gpu
+ * virtuals call cuDNN / cuBLAS / ad-hoc kernels.  Every entry point below is what one such
+ * Forward_gpu would bind instead; the reference call site it replaces is cited per function.
+ * INTEGRATION.md shows the Caffe-side Layer::Forward_gpu stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless named host_*;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every function returns MSCNN_OK (0) or a negative MSCNN_ERR_* code and never aborts;
+ *     the C++ Caffe-API mirror wraps them in CHECK_EQ(rc, 0) to keep Caffe's abort-on-error
+ *     convention (include/caffe/util/device_alternate.hpp:48-53);
+ *   - no CPU fallback exists: without a CUDA device the compute calls return MSCNN_ERR_CUDA.
+ *
+ * Activation storage ("planes")
+ *   Internal activations are NHWC bf16 with the channel count padded to a multiple of 64.
+ *   An fp32-faithful tensor is a PAIR of planes (hi, lo): x ~= hi + lo with hi = bf16(x),
+ *   lo = bf16(x - hi) (relative error <= 2^-17).  Passing lo == NULL everywhere selects the
+ *   plain bf16 path.  Caffe-visible blobs are NCHW fp32; the mscnn_nchw_* / mscnn_nhwc_*
+ *   converters move between the two.
+ */
+#ifndef MSCNN_B200_H_
+#define MSCNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSCNN_OK 0
+#define MSCNN_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define MSCNN_ERR_CUDA (-2)    /* CUDA runtime or driver error (message on stderr) */
+#define MSCNN_ERR_NOMEM (-3)
+
+#define MSCNN_OUT_NHWC_BF16 0 /* planes, via TMA store */
+#define MSCNN_OUT_NCHW_F32 1  /* Caffe blob layout, fp32 */
+
+#define MSCNN_POOL_MAX 0
+#define MSCNN_POOL_AVE 1
+
+#define MSCNN_NMS_IOU 0  /* intersection / union            */
+#define MSCNN_NMS_IOMU 1 /* intersection / min(area)        */
+#define MSCNN_NMS_IOFU 2 /* intersection / area(first box)  */
+
+#define MSCNN_MAX_SCALES 16
+
+/* library / device ------------------------------------------------------------------ */
+const char* mscnn_version(void);
+int mscnn_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Convolution (stride 1) / InnerProduct with fused bias and optional ReLU.
+ * Replaces ConvolutionLayer::Forward_gpu (src/caffe/layers/conv_layer.cu:8-23,
+ * cudnn_conv_layer.cu:11-46), InnerProductLayer::Forward_gpu (inner_product_layer.cu:10-31)
+ * and the in-place ReLULayer::Forward_gpu that follows them (relu_layer.cu:9-26).
+ *   x   : planes [N][H][W][C], C % 64 == 0
+ *   w   : planes [Cout_pad][KH][KW][C]  (mscnn_pack_conv_weights / mscnn_pack_fc_weights)
+ *   bias: fp32 [Cout_pad]
+ *   out : MSCNN_OUT_NHWC_BF16 -> y planes [N][Ho][Wo][Cout_pad] (Cout_pad % 64 == 0)
+ *         MSCNN_OUT_NCHW_F32  -> y_f32 [N][Cout][Ho][Wo]
+ *   Ho = H + 2 pad_h - KH + 1, Wo likewise.  InnerProduct = KH = KW = H = W = 1.
+ */
+typedef struct mscnn_conv_desc {
+  const void* x_hi;
+  const void* x_lo; /* NULL -> single-term bf16 */
+  int N, H, W, C;
+  const void* w_hi;
+  const void* w_lo;
+  const float* bias;
+  int Cout, Cout_pad, KH, KW, pad_h, pad_w;
+  int relu;
+  int out_mode;
+  void* y_hi;
+  void* y_lo; /* may be NULL even when x_lo is set (bf16-only output) */
+  float* y_f32;
+} mscnn_conv_desc;
+int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream);
+
+/* Weight packing (done once at load time; replaces nothing in the reference -- Caffe keeps
+ * [Cout][Cin][KH][KW] fp32, blob layout base_conv_layer.cpp:135-142).
+ *   conv: w_f32 [Cout][Cin][KH][KW] -> planes [Cout_pad][KH][KW][Cin_pad], zero padded.
+ *   fc  : w_f32 [Nout][C*H*W] (Caffe flattening c*H*W + h*W + w, inner_product_layer.cpp:32-48)
+ *         -> planes [Nout_pad][(h*W + w)*Cpad + c], the NHWC flattening of the bottom. */
+int mscnn_pack_conv_weights(const float* w_f32, void* w_hi, void* w_lo, int Cout, int Cin, int KH,
+                            int KW, int Cout_pad, int Cin_pad, void* stream);
+int mscnn_pack_fc_weights(const float* w_f32, void* w_hi, void* w_lo, int Nout, int C, int H, int W,
+                          int Nout_pad, int Cpad, void* stream);
+
+/* Layout converters between Caffe blobs (NCHW fp32, blob.hpp:153-164) and planes. */
+int mscnn_nchw_f32_to_planes(const float* x, void* hi, void* lo, int N, int C, int H, int W,
+                             int Cpad, void* stream);
+int mscnn_planes_to_nchw_f32(const void* hi, const void* lo, float* y, int N, int C, int H, int W,
+                             int Cpad, void* stream);
+/* conv1_1 operand: 3x3 / pad 1 patches of a 3-channel NCHW fp32 image as 64-channel planes,
+ * channel k = c*9 + dy*3 + dx for k < 27 (Caffe's own weight order), zero above. */
+int mscnn_im2col3x3_c3_to_planes(const float* x, void* hi, void* lo, int N, int H, int W,
+                                 void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCNN_B200_H_ */

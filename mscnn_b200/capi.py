@@ -1,0 +1,115 @@
+"""ctypes binding of the C ABI declared in include/mscnn_b200.h.
+
+This is plumbing only: it loads the in-tree ``libmscnn_b200.so`` (built by
+``python -m mscnn_b200.build``) and fails loudly when it is missing -- there is no Python or
+CPU fallback for any compute entry point.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "libmscnn_b200.so"
+
+OK = 0
+ERR_INVALID = -1
+ERR_CUDA = -2
+ERR_NOMEM = -3
+
+OUT_NHWC_BF16 = 0
+OUT_NCHW_F32 = 1
+POOL_MAX = 0
+POOL_AVE = 1
+NMS_IOU, NMS_IOMU, NMS_IOFU = 0, 1, 2
+MAX_SCALES = 16
+
+c_void_p, c_int, c_float = C.c_void_p, C.c_int, C.c_float
+
+
+class MscnnError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("x_hi", c_void_p), ("x_lo", c_void_p),
+        ("N", c_int), ("H", c_int), ("W", c_int), ("C", c_int),
+        ("w_hi", c_void_p), ("w_lo", c_void_p), ("bias", c_void_p),
+        ("Cout", c_int), ("Cout_pad", c_int), ("KH", c_int), ("KW", c_int),
+        ("pad_h", c_int), ("pad_w", c_int),
+        ("relu", c_int), ("out_mode", c_int),
+        ("y_hi", c_void_p), ("y_lo", c_void_p), ("y_f32", c_void_p),
+    ]
+
+
+class BoxOutputCfg(C.Structure):
+    _fields_ = [
+        ("num_scales", c_int),
+        ("channels", c_int),
+        ("height", c_int * MAX_SCALES), ("width", c_int * MAX_SCALES),
+        ("field_w", c_float * MAX_SCALES), ("field_h", c_float * MAX_SCALES),
+        ("downsample_rate", c_float * MAX_SCALES),
+        ("fg_thr", c_float), ("iou_thr", c_float), ("nms_type", c_int),
+        ("field_whr", c_float), ("field_xyr", c_float), ("min_size", c_float),
+        ("max_nms_num", c_int), ("max_post_nms_num", c_int),
+        ("do_bbox_norm", c_int),
+        ("bbox_mean", c_float * 4), ("bbox_std", c_float * 4),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the native library; raise if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise MscnnError(
+                f"{_LIB_PATH} is missing: run `python -m mscnn_b200.build` (nvcc, sm_100a). "
+                "There is no fallback implementation.")
+        _lib = C.CDLL(str(_LIB_PATH))
+        _declare(_lib)
+    return _lib
+
+
+def _declare(L: C.CDLL) -> None:
+    L.mscnn_version.restype = C.c_char_p
+    L.mscnn_version.argtypes = []
+    L.mscnn_sm_count.restype = c_int
+    L.mscnn_conv_forward.restype = c_int
+    L.mscnn_conv_forward.argtypes = [C.POINTER(ConvDesc), c_void_p]
+    L.mscnn_pack_conv_weights.restype = c_int
+    L.mscnn_pack_conv_weights.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]
+    L.mscnn_pack_fc_weights.restype = c_int
+    L.mscnn_pack_fc_weights.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]
+    L.mscnn_nchw_f32_to_planes.restype = c_int
+    L.mscnn_nchw_f32_to_planes.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]
+    L.mscnn_planes_to_nchw_f32.restype = c_int
+    L.mscnn_planes_to_nchw_f32.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]
+    L.mscnn_im2col3x3_c3_to_planes.restype = c_int
+    L.mscnn_im2col3x3_c3_to_planes.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]
+    for name in _OPTIONAL:
+        if hasattr(L, name):
+            getattr(L, name).restype = c_int
+
+
+# entry points added after the first slice; declared lazily so an older .so still loads
+_OPTIONAL = [
+    "mscnn_pool2x2_forward", "mscnn_upsample2x_forward", "mscnn_box_output_forward",
+    "mscnn_roi_pool_forward", "mscnn_detect_postprocess",
+]
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != OK:
+        raise MscnnError(f"{what or 'mscnn call'} failed with status {rc}")
+
+
+def ptr(t) -> int | None:
+    """Device/host address of a torch tensor or numpy array (None passes NULL)."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data

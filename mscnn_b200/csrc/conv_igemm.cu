@@ -1,0 +1,489 @@
+// Implicit-GEMM convolution / inner product on the sm_100a tensor cores.
+//
+// Replaces, for the MS-CNN forward path, the reference's
+//   ConvolutionLayer::Forward_{cpu,gpu}   (src/caffe/layers/conv_layer.cpp:25-40,
+//                                          base_conv_layer.cpp:257-280: im2col + sgemm + bias gemm)
+//   InnerProductLayer::Forward_{cpu,gpu}  (src/caffe/layers/inner_product_layer.cpp:84-97)
+//   ReLULayer::Forward_*                  (src/caffe/layers/relu_layer.cpp:9-19, fused here)
+//
+// Design (B200-first, not a translation of im2col+sgemm):
+//   * activations live in HBM as NHWC bf16 ("planes"); an fp32-faithful tensor is the pair
+//     (hi, lo) with x ~= hi + lo, |lo| <= ulp_bf16(hi)/2;
+//   * GEMM view: M = output pixels, N = output channels, K = taps x input channels.
+//     An M tile is a TMA box {64 ch, bw, bh, bn} with bw*bh*bn <= 128 pixels; the tap
+//     (dy,dx) operand is the same box shifted by (dx-pad, dy-pad): TMA zero-fills out-of-
+//     bounds pixels, which *is* the convolution's zero padding.  No im2col buffer exists.
+//   * tcgen05.mma (M=128, N=BLOCK_N, K=16, bf16 -> fp32) accumulates in TMEM; two TMEM
+//     accumulators are double buffered so the epilogue of tile i overlaps the MMAs of i+1.
+//   * fp32-faithful mode = three bf16 GEMM terms accumulated in the same TMEM tile:
+//     hi*hi + hi*lo + lo*hi (the dropped lo*lo term is < 2^-16 relative).
+//   * warp roles: warp0 = TMA producer, warp1 = MMA issuer (+TMEM alloc), warps2-5 =
+//     epilogue (TMEM -> regs -> bias/ReLU -> bf16 split -> swizzled smem -> TMA store, or
+//     direct fp32 NCHW stores for the narrow proposal / prediction heads).
+//   * persistent CTAs (one per SM), static round-robin tile schedule, n-tile fastest so
+//     CTAs working on the same pixels share the activation tile through L2.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "mscnn_b200.h"
+#include "ptx_sm100.cuh"
+#include "tmap.h"
+
+namespace mscnn {
+
+struct IgemmParams {
+  int num_terms;   // 1: bf16; 3: split-bf16 (hi*hi, hi*lo, lo*hi)
+  int taps_h, taps_w, pad_h, pad_w;
+  int cin_chunks;  // Cin_pad / 64
+  int tiles_w, tiles_h, tiles_n, n_tiles;
+  int box_w, box_h, box_n;
+  int relu;
+  int out_mode;    // MSCNN_OUT_NHWC_BF16 or MSCNN_OUT_NCHW_F32
+  int has_lo_out;
+  int stages, epi_bufs;
+  const float* bias;  // [Cout_pad]
+  float* out_f32;     // NCHW fp32 (out_mode 1)
+  int out_n, out_c, out_h, out_w;
+};
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;                       // bf16 elements = 128 B = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kEpiBarId = 1;
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
+                  const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB_hi,
+                  const __grid_constant__ CUtensorMap tmB_lo,
+                  const __grid_constant__ CUtensorMap tmO_hi,
+                  const __grid_constant__ CUtensorMap tmO_lo, const IgemmParams p) {
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two for 32..256
+  constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+
+  const int S = p.stages;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = sA + S * kABytes;
+  const uint32_t sEpi = sB + S * kBBytes;  // 1024-aligned: kABytes, kBBytes are multiples of 1024
+  const int epi_buf_bytes = kABytes * (p.has_lo_out ? 2 : 1);
+  const uint32_t sMisc = sEpi + p.epi_bufs * epi_buf_bytes;
+  uint8_t* misc_gen = smem_gen + (sMisc - smem_base);
+  float* bias_s = reinterpret_cast<float*>(misc_gen);  // BLOCK_N floats
+  const uint32_t sBar = sMisc + BLOCK_N * 4;
+  // barrier layout: full[S], empty[S], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return sBar + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return sBar + 8u * (2 * S + 2 + a); };
+  const uint32_t sTmemPtr = sBar + 8u * (2 * S + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(misc_gen + BLOCK_N * 4 + 8 * (2 * S + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tmap(&tmA_hi);
+    ptx::prefetch_tmap(&tmB_hi);
+    if (p.num_terms > 1) {
+      ptx::prefetch_tmap(&tmA_lo);
+      ptx::prefetch_tmap(&tmB_lo);
+    }
+    if (p.out_mode == MSCNN_OUT_NHWC_BF16) {
+      ptx::prefetch_tmap(&tmO_hi);
+      if (p.has_lo_out) ptx::prefetch_tmap(&tmO_lo);
+    }
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(full_bar(s), 1);
+      ptx::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(tfull_bar(a), 1);
+      ptx::mbar_init(tempty_bar(a), kEpiThreads);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(sTmemPtr, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
+  const int total_tiles = m_tiles * p.n_tiles;
+  const int num_kb = p.num_terms * p.taps_h * p.taps_w * p.cin_chunks;
+  const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * kBlockK * 2;
+
+  auto tile_coords = [&](int tile, int& n_tile, int& tw, int& th, int& tn) {
+    n_tile = tile % p.n_tiles;
+    int m = tile / p.n_tiles;
+    tw = m % p.tiles_w;
+    m /= p.tiles_w;
+    th = m % p.tiles_h;
+    tn = m / p.tiles_h;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int n_tile, tw, th, tn;
+        tile_coords(tile, n_tile, tw, th, tn);
+        const int w0 = tw * p.box_w - p.pad_w, h0 = th * p.box_h - p.pad_h, n0 = tn * p.box_n;
+        for (int term = 0; term < p.num_terms; ++term) {
+          const CUtensorMap* mapA = (term == 2) ? &tmA_lo : &tmA_hi;
+          const CUtensorMap* mapB = (term == 1) ? &tmB_lo : &tmB_hi;
+          for (int dy = 0; dy < p.taps_h; ++dy) {
+            for (int dx = 0; dx < p.taps_w; ++dx) {
+              const int tap = dy * p.taps_w + dx;
+              for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                ptx::mbar_expect_tx(full_bar(stage), a_box_bytes + kBBytes);
+                ptx::tma_load_4d(sA + stage * kABytes, mapA, full_bar(stage), cc * kBlockK,
+                                 w0 + dx, h0 + dy, n0);
+                ptx::tma_load_2d(sB + stage * kBBytes, mapB, full_bar(stage),
+                                 (tap * p.cin_chunks + cc) * kBlockK, n_tile * BLOCK_N);
+                if (++stage == S) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(full_bar(stage), phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = ptx::umma_desc_sw128(sA + stage * kABytes);
+          const uint64_t b_desc = ptx::umma_desc_sw128(sB + stage * kBBytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 B per UMMA_K step inside the 128 B swizzle atom -> +2 in the address field
+            ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc,
+                           (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs finish
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue
+    const int et = threadIdx.x - 64;         // 0..127
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int row = quarter * 32 + lane;     // accumulator row == tile pixel
+    const bool issuer = (et == 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int ebuf = 0;
+    const int hw_box = p.box_w * p.box_h;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int n_tile, tw, th, tn;
+      tile_coords(tile, n_tile, tw, th, tn);
+      const int n_base = n_tile * BLOCK_N;
+      // bias slice for this n tile (visible after the first named barrier below)
+      for (int j = et; j < BLOCK_N; j += kEpiThreads) bias_s[j] = p.bias[n_base + j];
+
+      ptx::mbar_wait(tfull_bar(acc), acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * BLOCK_N) +
+                             (static_cast<uint32_t>(quarter * 32) << 16);
+
+      if (p.out_mode == MSCNN_OUT_NHWC_BF16) {
+        if constexpr (BLOCK_N >= 64) {
+#pragma unroll 1
+          for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
+            uint32_t v[64];
+            ptx::tmem_ld_32x32(t_row + chunk * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+            ptx::tmem_ld_32x32(t_row + chunk * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+            // the staging buffer we are about to overwrite must have been read by its TMA store
+            if (issuer) {
+              if (p.epi_bufs == 1) ptx::tma_store_wait_read<0>();
+              else ptx::tma_store_wait_read<1>();
+            }
+            ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // also publishes bias_s
+            ptx::tmem_ld_wait();
+            const uint32_t buf = sEpi + ebuf * epi_buf_bytes;
+            const uint32_t row_hi = buf + row * 128;
+            const uint32_t row_lo = row_hi + kABytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // 8 x 16 B = 64 channels
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float f0 = __uint_as_float(v[j * 8 + 2 * q]) + bias_s[chunk * 64 + j * 8 + 2 * q];
+                float f1 =
+                    __uint_as_float(v[j * 8 + 2 * q + 1]) + bias_s[chunk * 64 + j * 8 + 2 * q + 1];
+                if (p.relu) {
+                  f0 = fmaxf(f0, 0.f);
+                  f1 = fmaxf(f1, 0.f);
+                }
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+                hi[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
+                lo[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+                        (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+              }
+              const uint32_t off = static_cast<uint32_t>((j ^ (row & 7)) << 4);  // 128B swizzle
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off),
+                           "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
+                           : "memory");
+              if (p.has_lo_out)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_lo + off),
+                             "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3])
+                             : "memory");
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(kEpiBarId, kEpiThreads);
+            if (issuer) {
+              const int c0 = n_base + chunk * 64;
+              ptx::tma_store_4d(&tmO_hi, buf, c0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+              if (p.has_lo_out)
+                ptx::tma_store_4d(&tmO_lo, buf + kABytes, c0, tw * p.box_w, th * p.box_h,
+                                  tn * p.box_n);
+              ptx::tma_store_commit();
+            }
+            if (++ebuf == p.epi_bufs) ebuf = 0;
+          }
+        }
+      } else {
+        // fp32 NCHW, direct stores: consecutive lanes are consecutive pixels of one channel.
+        ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // bias_s visible
+        const int dn = row / hw_box, rem = row - dn * hw_box;
+        const int dh = rem / p.box_w, dw = rem - dh * p.box_w;
+        const int n = tn * p.box_n + dn, h = th * p.box_h + dh, w = tw * p.box_w + dw;
+        const bool ok = (dn < p.box_n) && n < p.out_n && h < p.out_h && w < p.out_w;
+        const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
+        float* obase = p.out_f32 + (static_cast<size_t>(n) * p.out_c) * plane +
+                       static_cast<size_t>(h) * p.out_w + w;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_row + chunk * 32, v);
+          ptx::tmem_ld_wait();
+          if (ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int ch = n_base + chunk * 32 + j;
+              if (ch < p.out_c) {
+                float f = __uint_as_float(v[j]) + bias_s[chunk * 32 + j];
+                if (p.relu) f = fmaxf(f, 0.f);
+                obase[static_cast<size_t>(ch) * plane] = f;
+              }
+            }
+          }
+        }
+        ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // bias_s reuse hazard for the next tile
+      }
+      // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(tempty_bar(acc));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (issuer) ptx::tma_store_wait_all<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+
+static int pick_block_n(int cout_pad) {
+  if (cout_pad % 256 == 0) return 256;
+  if (cout_pad % 128 == 0) return 128;
+  if (cout_pad % 64 == 0) return 64;
+  return 32;
+}
+
+// Choose the pixel box (bw, bh, bn), bw*bh*bn <= 128, that wastes the fewest MMA rows.
+static void pick_box(int N, int Ho, int Wo, int* bw_o, int* bh_o, int* bn_o) {
+  double best = -1.0;
+  int b_w = 1, b_h = 1, b_n = 1;
+  for (int bw = 1; bw <= 128 && bw <= Wo; ++bw) {
+    for (int bh = 1; bh * bw <= 128 && bh <= Ho; ++bh) {
+      int bn = 128 / (bw * bh);
+      if (bn > N) bn = N;
+      // rows of a K-major SW128 tile come in groups of 8: any row count works for TMA, the
+      // MMA simply ignores the tail rows.
+      const long tiles = (long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh) * ((N + bn - 1) / bn);
+      const double eff = (double)N * Ho * Wo / (tiles * 128.0);
+      // prefer wider boxes on ties: longer contiguous runs for TMA
+      const double score = eff + 1e-6 * bw + 1e-9 * bh;
+      if (score > best) {
+        best = score;
+        b_w = bw;
+        b_h = bh;
+        b_n = bn;
+      }
+    }
+  }
+  *bw_o = b_w;
+  *bh_o = b_h;
+  *bn_o = b_n;
+}
+
+template <int BLOCK_N>
+static cudaError_t launch_igemm(const CUtensorMap maps[6], const IgemmParams& p, int grid,
+                                size_t smem, cudaStream_t stream) {
+  auto kern = conv_igemm_kernel<BLOCK_N>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  return cudaGetLastError();
+}
+
+}  // namespace mscnn
+
+using namespace mscnn;
+
+extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (!d || !d->x_hi || !d->w_hi || !d->bias) return MSCNN_ERR_INVALID;
+  if (d->C % 64 != 0) return MSCNN_ERR_INVALID;
+  const bool split = (d->x_lo != nullptr);
+  if (split && !d->w_lo) return MSCNN_ERR_INVALID;
+  const int Ho = d->H + 2 * d->pad_h - d->KH + 1;
+  const int Wo = d->W + 2 * d->pad_w - d->KW + 1;
+  if (Ho <= 0 || Wo <= 0 || d->N <= 0) return MSCNN_ERR_INVALID;
+  const int BN = pick_block_n(d->Cout_pad);
+  if (d->Cout_pad % BN != 0 || d->Cout > d->Cout_pad) return MSCNN_ERR_INVALID;
+  if (d->out_mode == MSCNN_OUT_NHWC_BF16 && (BN < 64 || !d->y_hi)) return MSCNN_ERR_INVALID;
+  if (d->out_mode == MSCNN_OUT_NCHW_F32 && !d->y_f32) return MSCNN_ERR_INVALID;
+
+  IgemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_terms = split ? 3 : 1;
+  p.taps_h = d->KH;
+  p.taps_w = d->KW;
+  p.pad_h = d->pad_h;
+  p.pad_w = d->pad_w;
+  p.cin_chunks = d->C / 64;
+  pick_box(d->N, Ho, Wo, &p.box_w, &p.box_h, &p.box_n);
+  p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
+  p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
+  p.tiles_n = (d->N + p.box_n - 1) / p.box_n;
+  p.n_tiles = d->Cout_pad / BN;
+  p.relu = d->relu;
+  p.out_mode = d->out_mode;
+  p.has_lo_out = (d->out_mode == MSCNN_OUT_NHWC_BF16 && d->y_lo != nullptr) ? 1 : 0;
+  p.bias = d->bias;
+  p.out_f32 = d->y_f32;
+  p.out_n = d->N;
+  p.out_c = d->Cout;
+  p.out_h = Ho;
+  p.out_w = Wo;
+
+  // shared memory plan
+  const int b_bytes = BN * kBlockK * 2;
+  const int stage_bytes = kABytes + b_bytes;
+  const int epi_unit = (d->out_mode == MSCNN_OUT_NHWC_BF16) ? kABytes * (p.has_lo_out ? 2 : 1) : 0;
+  const int misc = BN * 4 + 8 * (2 * 8 + 4) + 16 + 1024 /*alignment slack*/;
+  const int budget = 227 * 1024;
+  int epi_bufs = (epi_unit == 0) ? 0 : 2;
+  int stages = (budget - misc - epi_bufs * epi_unit) / stage_bytes;
+  if (stages < 4 && epi_bufs == 2) {
+    epi_bufs = 1;
+    stages = (budget - misc - epi_bufs * epi_unit) / stage_bytes;
+  }
+  if (stages > 8) stages = 8;
+  if (stages < 2) return MSCNN_ERR_INVALID;
+  p.stages = stages;
+  p.epi_bufs = epi_bufs > 0 ? epi_bufs : 1;
+  const size_t smem = (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
+
+  CUtensorMap maps[6];
+  memset(maps, 0, sizeof(maps));
+  const uint32_t abox[4] = {64u, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
+  const uint64_t adim[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
+  int rc = tmap_nhwc_bf16(&maps[0], d->x_hi, adim, abox);
+  if (rc) return rc;
+  if (split) {
+    rc = tmap_nhwc_bf16(&maps[1], d->x_lo, adim, abox);
+    if (rc) return rc;
+  } else {
+    maps[1] = maps[0];
+  }
+  const uint64_t ktot = (uint64_t)d->KH * d->KW * d->C;
+  rc = tmap_2d_bf16(&maps[2], d->w_hi, ktot, (uint64_t)d->Cout_pad, 64u, (uint32_t)BN);
+  if (rc) return rc;
+  if (split) {
+    rc = tmap_2d_bf16(&maps[3], d->w_lo, ktot, (uint64_t)d->Cout_pad, 64u, (uint32_t)BN);
+    if (rc) return rc;
+  } else {
+    maps[3] = maps[2];
+  }
+  if (d->out_mode == MSCNN_OUT_NHWC_BF16) {
+    const uint64_t odim[4] = {(uint64_t)d->Cout_pad, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->N};
+    rc = tmap_nhwc_bf16(&maps[4], d->y_hi, odim, abox);
+    if (rc) return rc;
+    if (p.has_lo_out) {
+      rc = tmap_nhwc_bf16(&maps[5], d->y_lo, odim, abox);
+      if (rc) return rc;
+    } else {
+      maps[5] = maps[4];
+    }
+  } else {
+    maps[4] = maps[0];
+    maps[5] = maps[0];
+  }
+
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  int grid = mscnn_sm_count();
+  if (grid > total_tiles) grid = total_tiles;
+  cudaError_t e;
+  switch (BN) {
+    case 256: e = launch_igemm<256>(maps, p, grid, smem, stream); break;
+    case 128: e = launch_igemm<128>(maps, p, grid, smem, stream); break;
+    case 64: e = launch_igemm<64>(maps, p, grid, smem, stream); break;
+    default: e = launch_igemm<32>(maps, p, grid, smem, stream); break;
+  }
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mscnn_conv_forward: launch failed: %s\n", cudaGetErrorString(e));
+    return MSCNN_ERR_CUDA;
+  }
+  return MSCNN_OK;
+}

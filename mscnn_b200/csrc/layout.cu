@@ -1,0 +1,227 @@
+// Layout converters and weight packers (HBM-bound, coalesced on both sides through a
+// shared-memory transpose).  See include/mscnn_b200.h for the contracts.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mscnn_b200.h"
+
+namespace mscnn {
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// grid: (ceil(W/32), H, N * ceil(Cpad/64)); block 256 = 8 warps.
+// read:  x[n][c][h][w0..w0+31]  (lanes along w, warps along c)       -> coalesced 128 B
+// write: hi[n][h][w][c0..c0+63] (lanes along c pairs, warps along w) -> coalesced 128 B
+__global__ void nchw_to_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, int N, int C, int H, int W,
+                                      int Cpad) {
+  __shared__ float tile[64][33];
+  const int cblocks = Cpad / 64;
+  const int n = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 64;
+  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int cc = warp; cc < 64; cc += 8) {
+    const int c = c0 + cc, w = w0 + lane;
+    float v = 0.f;
+    if (c < C && w < W) v = x[((size_t)(n * C + c) * H + h) * W + w];
+    tile[cc][lane] = v;
+  }
+  __syncthreads();
+  for (int ww = warp; ww < 32; ww += 8) {
+    const int w = w0 + ww;
+    if (w >= W) continue;
+    const float v0 = tile[2 * lane][ww], v1 = tile[2 * lane + 1][ww];
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v0, h0, l0);
+    split_bf16(v1, h1, l1);
+    const size_t o = ((size_t)(n * H + h) * W + w) * Cpad + c0 + 2 * lane;
+    *reinterpret_cast<__nv_bfloat162*>(hi + o) = __nv_bfloat162(h0, h1);
+    if (lo) *reinterpret_cast<__nv_bfloat162*>(lo + o) = __nv_bfloat162(l0, l1);
+  }
+}
+
+__global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi,
+                                      const __nv_bfloat16* __restrict__ lo, float* __restrict__ y,
+                                      int N, int C, int H, int W, int Cpad) {
+  __shared__ float tile[64][33];
+  const int cblocks = Cpad / 64;
+  const int n = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 64;
+  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int ww = warp; ww < 32; ww += 8) {
+    const int w = w0 + ww;
+    float v0 = 0.f, v1 = 0.f;
+    if (w < W) {
+      const size_t o = ((size_t)(n * H + h) * W + w) * Cpad + c0 + 2 * lane;
+      const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(hi + o);
+      v0 = __bfloat162float(a.x);
+      v1 = __bfloat162float(a.y);
+      if (lo) {
+        const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(lo + o);
+        v0 += __bfloat162float(b.x);
+        v1 += __bfloat162float(b.y);
+      }
+    }
+    tile[2 * lane][ww] = v0;
+    tile[2 * lane + 1][ww] = v1;
+  }
+  __syncthreads();
+  for (int cc = warp; cc < 64; cc += 8) {
+    const int c = c0 + cc, w = w0 + lane;
+    if (c < C && w < W) y[((size_t)(n * C + c) * H + h) * W + w] = tile[cc][lane];
+  }
+}
+
+// One thread per pixel; 27 taps gathered from the 3-channel image, written as one 128 B row
+// per plane (eight 16 B stores).
+__global__ void im2col3x3_c3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, int N, int H, int W) {
+  const size_t total = (size_t)N * H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = idx % W;
+  const int h = (idx / W) % H;
+  const int n = idx / ((size_t)W * H);
+  __align__(16) __nv_bfloat16 vh[64];
+  __align__(16) __nv_bfloat16 vl[64];
+#pragma unroll
+  for (int k = 0; k < 64; ++k) {
+    vh[k] = __float2bfloat16_rn(0.f);
+    vl[k] = vh[k];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const int hh = h + dy - 1, ww = w + dx - 1;
+        float v = 0.f;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((size_t)(n * 3 + c) * H + hh) * W + ww];
+        split_bf16(v, vh[c * 9 + dy * 3 + dx], vl[c * 9 + dy * 3 + dx]);
+      }
+    }
+  }
+  uint4* oh = reinterpret_cast<uint4*>(hi + idx * 64);
+  const uint4* sh = reinterpret_cast<const uint4*>(vh);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) oh[j] = sh[j];
+  if (lo) {
+    uint4* ol = reinterpret_cast<uint4*>(lo + idx * 64);
+    const uint4* sl = reinterpret_cast<const uint4*>(vl);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ol[j] = sl[j];
+  }
+}
+
+// out[(co*KH*KW + tap)*Cin_pad + ci] = w[((co*Cin + ci)*KH*KW) + tap]
+__global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int taps,
+                                   int Cout_pad, int Cin_pad) {
+  const size_t total = (size_t)Cout_pad * taps * Cin_pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = i % Cin_pad;
+    const int tap = (i / Cin_pad) % taps;
+    const int co = i / ((size_t)Cin_pad * taps);
+    float v = 0.f;
+    if (co < Cout && ci < Cin) v = w[((size_t)co * Cin + ci) * taps + tap];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// out[no][(hw)*Cpad + c] = w[no][c*HW + hw]
+__global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                 __nv_bfloat16* __restrict__ lo, int Nout, int C, int HW,
+                                 int Nout_pad, int Cpad) {
+  const size_t total = (size_t)Nout_pad * HW * Cpad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int c = i % Cpad;
+    const int hw = (i / Cpad) % HW;
+    const int no = i / ((size_t)Cpad * HW);
+    float v = 0.f;
+    if (no < Nout && c < C) v = w[(size_t)no * C * HW + (size_t)c * HW + hw];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mscnn: %s launch failed: %s\n", what, cudaGetErrorString(e));
+    return MSCNN_ERR_CUDA;
+  }
+  return MSCNN_OK;
+}
+
+}  // namespace mscnn
+
+using namespace mscnn;
+
+extern "C" const char* mscnn_version(void) { return "mscnn_b200 0.1 (sm_100a)"; }
+
+extern "C" int mscnn_nchw_f32_to_planes(const float* x, void* hi, void* lo, int N, int C, int H,
+                                        int W, int Cpad, void* stream) {
+  if (!x || !hi || N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad % 64 || Cpad < C)
+    return MSCNN_ERR_INVALID;
+  if ((long)N * (Cpad / 64) > 65535 || H > 65535) return MSCNN_ERR_INVALID;
+  dim3 grid((W + 31) / 32, H, N * (Cpad / 64));
+  nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, C, H, W, Cpad);
+  return check_launch("nchw_to_planes");
+}
+
+extern "C" int mscnn_planes_to_nchw_f32(const void* hi, const void* lo, float* y, int N, int C,
+                                        int H, int W, int Cpad, void* stream) {
+  if (!y || !hi || N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad % 64 || Cpad < C)
+    return MSCNN_ERR_INVALID;
+  if ((long)N * (Cpad / 64) > 65535 || H > 65535) return MSCNN_ERR_INVALID;
+  dim3 grid((W + 31) / 32, H, N * (Cpad / 64));
+  planes_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, y, N, C, H, W, Cpad);
+  return check_launch("planes_to_nchw");
+}
+
+extern "C" int mscnn_im2col3x3_c3_to_planes(const float* x, void* hi, void* lo, int N, int H, int W,
+                                            void* stream) {
+  if (!x || !hi || N <= 0 || H <= 0 || W <= 0) return MSCNN_ERR_INVALID;
+  const size_t total = (size_t)N * H * W;
+  const int threads = 128;
+  im2col3x3_c3_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
+                        (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, H, W);
+  return check_launch("im2col3x3_c3");
+}
+
+extern "C" int mscnn_pack_conv_weights(const float* w, void* hi, void* lo, int Cout, int Cin, int KH,
+                                       int KW, int Cout_pad, int Cin_pad, void* stream) {
+  if (!w || !hi || Cout <= 0 || Cin <= 0 || Cout_pad < Cout || Cin_pad < Cin || Cin_pad % 64)
+    return MSCNN_ERR_INVALID;
+  const size_t total = (size_t)Cout_pad * KH * KW * Cin_pad;
+  const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  pack_conv_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout, Cin, KH * KW, Cout_pad, Cin_pad);
+  return check_launch("pack_conv_w");
+}
+
+extern "C" int mscnn_pack_fc_weights(const float* w, void* hi, void* lo, int Nout, int C, int H,
+                                     int W, int Nout_pad, int Cpad, void* stream) {
+  if (!w || !hi || Nout <= 0 || C <= 0 || Nout_pad < Nout || Cpad < C || Cpad % 64)
+    return MSCNN_ERR_INVALID;
+  const size_t total = (size_t)Nout_pad * H * W * Cpad;
+  const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  pack_fc_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Nout, C, H * W, Nout_pad, Cpad);
+  return check_launch("pack_fc_w");
+}

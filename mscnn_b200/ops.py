@@ -1,0 +1,142 @@
+"""Thin torch-tensor conveniences over the C ABI (used by tests, bench.py and the Python
+mirror of the Caffe Net).  torch is used for device memory and streams only; every function
+here ends in exactly one C-ABI call and raises if the native library is missing.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import capi
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def pad64(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+@dataclass
+class Planes:
+    """NHWC bf16 activation planes [N][H][W][Cpad]; ``lo`` is None on the plain-bf16 path."""
+    hi: torch.Tensor
+    lo: torch.Tensor | None
+    channels: int  # logical channel count (<= Cpad)
+
+    @property
+    def shape(self):
+        return tuple(self.hi.shape)
+
+    def float(self) -> torch.Tensor:
+        v = self.hi.float()
+        if self.lo is not None:
+            v = v + self.lo.float()
+        return v[..., : self.channels]
+
+
+@dataclass
+class PackedWeights:
+    hi: torch.Tensor          # [Cout_pad][KH][KW][Cin_pad] bf16
+    lo: torch.Tensor | None
+    bias: torch.Tensor        # fp32 [Cout_pad]
+    cout: int
+    kh: int
+    kw: int
+
+
+def nchw_to_planes(x: torch.Tensor, split: bool) -> Planes:
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, c, h, w = x.shape
+    cp = pad64(c)
+    hi = torch.empty((n, h, w, cp), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi) if split else None
+    capi.check(capi.lib().mscnn_nchw_f32_to_planes(capi.ptr(x), capi.ptr(hi), capi.ptr(lo),
+                                                   n, c, h, w, cp, _stream()), "nchw_f32_to_planes")
+    return Planes(hi, lo, c)
+
+
+def planes_to_nchw(p: Planes) -> torch.Tensor:
+    n, h, w, cp = p.hi.shape
+    y = torch.empty((n, p.channels, h, w), dtype=torch.float32, device=p.hi.device)
+    capi.check(capi.lib().mscnn_planes_to_nchw_f32(capi.ptr(p.hi), capi.ptr(p.lo), capi.ptr(y),
+                                                   n, p.channels, h, w, cp, _stream()),
+               "planes_to_nchw_f32")
+    return y
+
+
+def im2col3x3_c3(x: torch.Tensor, split: bool) -> Planes:
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3
+    n, _, h, w = x.shape
+    hi = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi) if split else None
+    capi.check(capi.lib().mscnn_im2col3x3_c3_to_planes(capi.ptr(x), capi.ptr(hi), capi.ptr(lo),
+                                                       n, h, w, _stream()), "im2col3x3_c3")
+    return Planes(hi, lo, 27)
+
+
+def pack_conv_weights(w: torch.Tensor, b: torch.Tensor | None, split: bool,
+                      cout_pad: int | None = None, cin_pad: int | None = None) -> PackedWeights:
+    """w: [Cout][Cin][KH][KW] fp32 (Caffe blob 0), b: [Cout] fp32 (blob 1) or None."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 4
+    cout, cin, kh, kw = w.shape
+    cout_pad = cout_pad or (pad64(cout) if cout > 32 else 32)
+    cin_pad = cin_pad or pad64(cin)
+    hi = torch.empty((cout_pad, kh, kw, cin_pad), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if split else None
+    capi.check(capi.lib().mscnn_pack_conv_weights(capi.ptr(w), capi.ptr(hi), capi.ptr(lo), cout, cin,
+                                                  kh, kw, cout_pad, cin_pad, _stream()),
+               "pack_conv_weights")
+    bias = torch.zeros(cout_pad, dtype=torch.float32, device=w.device)
+    if b is not None:
+        bias[:cout] = b
+    return PackedWeights(hi, lo, bias, cout, kh, kw)
+
+
+def pack_fc_weights(w: torch.Tensor, b: torch.Tensor | None, split: bool, c: int, h: int, wd: int,
+                    nout_pad: int | None = None) -> PackedWeights:
+    """w: [Nout][c*h*wd] fp32 in Caffe's NCHW flattening of the bottom blob."""
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 2
+    nout = w.shape[0]
+    assert w.shape[1] == c * h * wd
+    nout_pad = nout_pad or (pad64(nout) if nout > 32 else 32)
+    cp = pad64(c)
+    hi = torch.empty((nout_pad, 1, 1, h * wd * cp), dtype=torch.bfloat16, device=w.device)
+    lo = torch.empty_like(hi) if split else None
+    capi.check(capi.lib().mscnn_pack_fc_weights(capi.ptr(w), capi.ptr(hi), capi.ptr(lo), nout, c, h,
+                                                wd, nout_pad, cp, _stream()), "pack_fc_weights")
+    bias = torch.zeros(nout_pad, dtype=torch.float32, device=w.device)
+    if b is not None:
+        bias[:nout] = b
+    return PackedWeights(hi, lo, bias, nout, 1, 1)
+
+
+def conv_forward(x: Planes, w: PackedWeights, pad: int, relu: bool, out_f32: bool = False,
+                 out_split: bool | None = None):
+    """Convolution (stride 1) + bias (+ReLU).  Returns Planes, or an NCHW fp32 tensor when
+    ``out_f32``.  An InnerProduct is the KH=KW=H=W=1 case."""
+    n, h, wd, c = x.hi.shape
+    assert w.hi.shape[3] == c, (w.hi.shape, x.hi.shape)
+    ho, wo = h + 2 * pad - w.kh + 1, wd + 2 * pad - w.kw + 1
+    cout_pad = w.hi.shape[0]
+    d = capi.ConvDesc()
+    d.x_hi, d.x_lo = capi.ptr(x.hi), capi.ptr(x.lo)
+    d.N, d.H, d.W, d.C = n, h, wd, c
+    d.w_hi, d.w_lo, d.bias = capi.ptr(w.hi), capi.ptr(w.lo), capi.ptr(w.bias)
+    d.Cout, d.Cout_pad, d.KH, d.KW, d.pad_h, d.pad_w = w.cout, cout_pad, w.kh, w.kw, pad, pad
+    d.relu = int(relu)
+    if out_f32:
+        y = torch.empty((n, w.cout, ho, wo), dtype=torch.float32, device=x.hi.device)
+        d.out_mode, d.y_f32 = capi.OUT_NCHW_F32, capi.ptr(y)
+        out = y
+    else:
+        if out_split is None:
+            out_split = x.lo is not None
+        y_hi = torch.empty((n, ho, wo, cout_pad), dtype=torch.bfloat16, device=x.hi.device)
+        y_lo = torch.empty_like(y_hi) if out_split else None
+        d.out_mode, d.y_hi, d.y_lo = capi.OUT_NHWC_BF16, capi.ptr(y_hi), capi.ptr(y_lo)
+        out = Planes(y_hi, y_lo, w.cout)
+    capi.check(capi.lib().mscnn_conv_forward(d, _stream()), "conv_forward")
+    return out
