@@ -432,7 +432,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (stages > 8) stages = 8;
   if (stages < 2) return MSCNN_ERR_INVALID;
   p.stages = stages;
-  p.epi_bufs = epi_bufs > 0 ? epi_bufs : 1;
+  p.epi_bufs = epi_bufs;  // 0 in fp32-output mode: no staging region is carved
   const size_t smem = (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
 
   CUtensorMap maps[6];
