@@ -101,6 +101,85 @@ int mscnn_planes_to_nchw_f32(const void* hi, const void* lo, float* y, int N, in
 int mscnn_im2col3x3_c3_to_planes(const float* x, void* hi, void* lo, int N, int H, int W,
                                  void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Pooling, pad 0, ceil-mode output size.  Replaces PoolingLayer::Forward_gpu
+ * (src/caffe/layers/pooling_layer.cu:158-190; shape pooling_layer.cpp:79-123).
+ *   x planes [N][H][W][C] (C % 8 == 0) -> y planes [N][Ho][Wo][C],
+ *   Ho = ceil((H - kernel) / stride) + 1.  mode = MSCNN_POOL_MAX | MSCNN_POOL_AVE. */
+int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H, int W,
+                       int C, int kernel, int stride, int mode, void* stream);
+
+/* Depthwise transposed convolution, kernel 4 / stride 2 / pad 1 / group == channels / no bias:
+ * the "conv4_3_2x" layer of the -2x nets.  Replaces DeconvolutionLayer::Forward_gpu
+ * (src/caffe/layers/deconv_layer.cu) for that shape.  w: fp32 [Creal][1][4][4] (layer blob 0).
+ *   x planes [N][H][W][C] -> y planes [N][2H][2W][C]. */
+int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo,
+                           int N, int H, int W, int C, int Creal, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * BoxOutput: anchor decode + score, joint top-N over all scales, greedy NMS, outputs.
+ * Replaces BoxOutputLayer::Forward_cpu (src/caffe/layers/box_output_layer.cpp:66-234; the
+ * reference has no GPU version) with parameters of BoxOutputParameter / BBoxRegParameter
+ * (src/caffe/proto/caffe.proto:1315-1329,1346-1350).
+ *   maps[j]        : fp32 [N][channels][height[j]][width[j]], channels = cls_num + 4
+ *   proposals      : fp32 [rows][5] = [img x1 y1 x2 y2]      (top[0]), capacity N*max_nms_num rows
+ *   proposals_score: fp32 [rows][6] = [... score] (top[1]) or NULL
+ *   num_out (device int[2+N]): [0] rows in the blobs (>= 1: a dummy ROI [0 1 1 10 10] / zero
+ *                  row is emitted when nothing survives, :195-199,214-218), [1] true proposal
+ *                  count, [2+n] proposals of image n.
+ * max_nms_num must be in 1..8192 (the reference's 0 = "unbounded" is not supported on device). */
+typedef struct mscnn_box_output_cfg {
+  int num_scales;
+  int channels;
+  int height[MSCNN_MAX_SCALES], width[MSCNN_MAX_SCALES];
+  float field_w[MSCNN_MAX_SCALES], field_h[MSCNN_MAX_SCALES], downsample_rate[MSCNN_MAX_SCALES];
+  float fg_thr, iou_thr;
+  int nms_type; /* MSCNN_NMS_* */
+  float field_whr, field_xyr, min_size;
+  int max_nms_num, max_post_nms_num;
+  int do_bbox_norm;
+  float bbox_mean[4], bbox_std[4];
+} mscnn_box_output_cfg;
+int mscnn_box_output_workspace_bytes(const mscnn_box_output_cfg* cfg, int N, size_t* bytes);
+int mscnn_box_output_forward(const mscnn_box_output_cfg* cfg, int N, const float* const* maps /*host array*/,
+                             void* workspace, size_t workspace_bytes, float* proposals,
+                             float* proposals_score, int* num_out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * ROIPooling with the MS-CNN pad_ratio context extension, writing at a channel offset of a wider
+ * output so that org || ctx are concatenated in place.  Replaces ROIPoolingLayer::Forward_gpu
+ * (src/caffe/layers/roi_pooling_layer.cu:19-104; CPU semantics roi_pooling_layer.cpp:49-139) and
+ * ConcatLayer::Forward_gpu (concat_layer.cu:28-46).
+ *   x planes [N][H][W][C]; rois fp32 [R][5] = [img x1 y1 x2 y2];
+ *   y planes [R][pooled_h][pooled_w][out_channels_total], channels [offset, offset + C). */
+int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                           const float* rois, int R, int pooled_h, int pooled_w, float spatial_scale,
+                           float pad_ratio, void* y_hi, void* y_lo, int out_channels_total,
+                           int out_channel_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Final detections for one class: softmax probability, bbox-delta decode, clip, greedy NMS.
+ * Replaces the MATLAB code after net.forward in the reference driver
+ * (examples/kitti_car/run_mscnn_detection.m:75-120, utils/bbNms.m:112-126).
+ *   proposals_score [R][6], cls_pred [R][num_cls], bbox_pred [R][4*num_cls], num_rois = the
+ *   num_out array written by mscnn_box_output_forward (per-image row ranges).
+ *   dets fp32 [N][max_rois_per_image][5] = [x y w h prob] in kept order; det_counts int[N]. */
+typedef struct mscnn_detect_cfg {
+  int num_cls;
+  int cls_id; /* 1-based, 2 = car in the KITTI nets */
+  float bbox_mean[4], bbox_std[4];
+  float proposal_thr; /* -10 */
+  float nms_overlap;  /* 0.5 */
+  float ratio_h, ratio_w; /* net input size / original image size */
+  float org_h, org_w;
+  int max_rois_per_image; /* 1..8192 */
+} mscnn_detect_cfg;
+int mscnn_detect_workspace_bytes(const mscnn_detect_cfg* cfg, int N, size_t* bytes);
+int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
+                             const float* cls_pred, const float* bbox_pred, const int* num_rois,
+                             void* workspace, size_t workspace_bytes, float* dets, int* det_counts,
+                             void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -57,6 +57,16 @@ class BoxOutputCfg(C.Structure):
     ]
 
 
+class DetectCfg(C.Structure):
+    _fields_ = [
+        ("num_cls", c_int), ("cls_id", c_int),
+        ("bbox_mean", c_float * 4), ("bbox_std", c_float * 4),
+        ("proposal_thr", c_float), ("nms_overlap", c_float),
+        ("ratio_h", c_float), ("ratio_w", c_float), ("org_h", c_float), ("org_w", c_float),
+        ("max_rois_per_image", c_int),
+    ]
+
+
 _lib = None
 
 
@@ -89,16 +99,24 @@ def _declare(L: C.CDLL) -> None:
     L.mscnn_planes_to_nchw_f32.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]
     L.mscnn_im2col3x3_c3_to_planes.restype = c_int
     L.mscnn_im2col3x3_c3_to_planes.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 3 + [c_void_p]
-    for name in _OPTIONAL:
-        if hasattr(L, name):
-            getattr(L, name).restype = c_int
-
-
-# entry points added after the first slice; declared lazily so an older .so still loads
-_OPTIONAL = [
-    "mscnn_pool2x2_forward", "mscnn_upsample2x_forward", "mscnn_box_output_forward",
-    "mscnn_roi_pool_forward", "mscnn_detect_postprocess",
-]
+    L.mscnn_pool_forward.restype = c_int
+    L.mscnn_pool_forward.argtypes = [c_void_p] * 4 + [c_int] * 7 + [c_void_p]
+    L.mscnn_deconv2x_forward.restype = c_int
+    L.mscnn_deconv2x_forward.argtypes = [c_void_p] * 5 + [c_int] * 5 + [c_void_p]
+    L.mscnn_box_output_workspace_bytes.restype = c_int
+    L.mscnn_box_output_workspace_bytes.argtypes = [C.POINTER(BoxOutputCfg), c_int, C.POINTER(C.c_size_t)]
+    L.mscnn_box_output_forward.restype = c_int
+    L.mscnn_box_output_forward.argtypes = [C.POINTER(BoxOutputCfg), c_int, C.POINTER(c_void_p), c_void_p,
+                                           C.c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.mscnn_roi_pool_forward.restype = c_int
+    L.mscnn_roi_pool_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                         c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_int,
+                                         c_void_p]
+    L.mscnn_detect_workspace_bytes.restype = c_int
+    L.mscnn_detect_workspace_bytes.argtypes = [C.POINTER(DetectCfg), c_int, C.POINTER(C.c_size_t)]
+    L.mscnn_detect_postprocess.restype = c_int
+    L.mscnn_detect_postprocess.argtypes = [C.POINTER(DetectCfg), c_int] + [c_void_p] * 5 + [C.c_size_t] + \
+        [c_void_p] * 3
 
 
 def check(rc: int, what: str = "") -> None:

@@ -1,0 +1,684 @@
+// BoxOutput on the device: anchor decode + objectness score, per-image joint top-N over all
+// scales, greedy NMS, and the [R,5] / [R,6] outputs -- without the host round trip the
+// reference makes (BoxOutputLayer has only Forward_cpu:
+// /root/reference/include/caffe/layers/box_output_layer.hpp:37-40, so GPU mode falls back to
+// src/caffe/layers/box_output_layer.cpp:66-234 through layer.hpp:341-345).
+//
+// Parity notes (every discrete decision of the reference is reproduced bit for bit):
+//   * all box arithmetic is fp32 with one rounding per operation (the file is compiled with
+//     -fmad=false; the reference is scalar x86-64 code without FMA);
+//   * exp() is evaluated in fp64 and rounded once to fp32, which agrees with glibc's expf (the
+//     function the reference resolves to for Dtype=float) except on sub-ulp ties;
+//   * ranking is std::sort with std::greater<pair<score,idx>> (box_output_layer.cpp:168): score
+//     descending, ties broken by the LARGER candidate index.  Candidate indices grow with the
+//     anchor scan order (scale j, then row-major position), so the 64-bit key
+//     (orderable(score) << 32 | anchor_index) sorted descending gives the same permutation;
+//   * NMS is nmsMax(greedy) over the top max_nms_num boxes of an image, all scales together
+//     (box_output_layer.cpp:38-63,176-182), IoU by BoxIOU (util/math_functions.cpp:13-35) with
+//     the strict `>` test.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mscnn_b200.h"
+
+namespace mscnn {
+
+struct DecodeScale {
+  const float* data;  // [N][C][H][W]
+  int height, width;
+  int anchor_base;    // first anchor index of this scale inside an image
+  float field_w, field_h, rate;
+  float img_w, img_h;  // (float)(int)(width * rate)
+};
+
+struct DecodeParams {
+  DecodeScale sc[MSCNN_MAX_SCALES];
+  int num_scales, channels, cls_num, anchors_per_image;
+  float fg_thr, min_xyr, max_xyr, min_whr, max_whr, min_size;
+  int do_norm;
+  float mean[4], stdv[4];
+};
+
+__device__ __forceinline__ uint32_t float_orderable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float orderable_float(uint32_t o) {
+  const uint32_t u = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ float exp_ref(float x) { return static_cast<float>(exp(static_cast<double>(x))); }
+
+// One thread per anchor; channel planes are read with unit stride across the warp.
+// box_output_layer.cpp:107-163.
+__global__ void box_decode_kernel(const DecodeParams p, int N, unsigned long long* __restrict__ keys,
+                                  float4* __restrict__ boxes) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = blockIdx.y;
+  if (a >= p.anchors_per_image) return;
+  int j = 0;
+#pragma unroll 1
+  for (int s = 1; s < p.num_scales; ++s)
+    if (a >= p.sc[s].anchor_base) j = s;
+  const DecodeScale& S = p.sc[j];
+  const int id = a - S.anchor_base;
+  const int spatial = S.height * S.width;
+  const float* x = S.data + (size_t)n * p.channels * spatial + id;
+  const int h = id / S.width, w = id - h * S.width;
+
+  float fg = -3.402823466e+38f;  // -FLT_MAX
+  for (int k = 1; k < p.cls_num; ++k) {
+    const float v = x[(size_t)k * spatial];
+    fg = (fg < v) ? v : fg;  // std::max(fg, v)
+  }
+  fg = fg - x[0];
+  unsigned long long key = 0ull;
+  if (fg >= p.fg_thr) {
+    const float* c = x + (size_t)p.cls_num * spatial;
+    float bx = c[0], by = c[(size_t)spatial], bw = c[(size_t)2 * spatial], bh = c[(size_t)3 * spatial];
+    if (p.do_norm) {
+      bx = bx * p.stdv[0]; by = by * p.stdv[1]; bw = bw * p.stdv[2]; bh = bh * p.stdv[3];
+      bx = bx + p.mean[0]; by = by + p.mean[1]; bw = bw + p.mean[2]; bh = bh + p.mean[3];
+    }
+    bx = (p.min_xyr < bx) ? bx : p.min_xyr; bx = (bx < p.max_xyr) ? bx : p.max_xyr;
+    by = (p.min_xyr < by) ? by : p.min_xyr; by = (by < p.max_xyr) ? by : p.max_xyr;
+    bx = bx * S.field_w + ((float)w + 0.5f) * S.rate;
+    by = by * S.field_h + ((float)h + 0.5f) * S.rate;
+    bw = (p.min_whr < bw) ? bw : p.min_whr; bw = (bw < p.max_whr) ? bw : p.max_whr;
+    bh = (p.min_whr < bh) ? bh : p.min_whr; bh = (bh < p.max_whr) ? bh : p.max_whr;
+    bw = S.field_w * exp_ref(bw);
+    bh = S.field_h * exp_ref(bh);
+    bx = bx - bw / 2.0f;
+    by = by - bh / 2.0f;
+    bx = (bx < 0.0f) ? 0.0f : bx;  // std::max(bbx, 0)
+    by = (by < 0.0f) ? 0.0f : by;
+    const float rw = S.img_w - bx, rh = S.img_h - by;
+    bw = (rw < bw) ? rw : bw;  // std::min(bbw, img_width - bbx)
+    bh = (rh < bh) ? rh : bh;
+    if (bw >= p.min_size && bh >= p.min_size) {
+      key = ((unsigned long long)float_orderable(fg) << 32) | (unsigned int)a;
+      boxes[(size_t)n * p.anchors_per_image + a] = make_float4(bx, by, bw, bh);
+    }
+  }
+  keys[(size_t)n * p.anchors_per_image + a] = key;
+}
+
+// ----------------------------------------------------------------------------------------
+// Per image: the K largest keys (K = max_nms_num), sorted descending.  One 1024-thread CTA per
+// image: byte-wise radix select of the K-th largest key, compaction of keys >= threshold into
+// shared memory, bitonic sort.  box_output_layer.cpp:166-179.
+constexpr int kTopkThreads = 1024;
+
+__global__ void __launch_bounds__(kTopkThreads)
+box_topk_kernel(const unsigned long long* __restrict__ keys, const float4* __restrict__ boxes,
+                int A, int K, int Kpad, float4* __restrict__ sorted_boxes,
+                float* __restrict__ sorted_scores, int* __restrict__ counts) {
+  extern __shared__ unsigned long long sk[];  // Kpad keys
+  __shared__ unsigned int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_valid, s_fill;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const unsigned long long* kk = keys + (size_t)n * A;
+
+  if (tid == 0) { s_valid = 0; s_fill = 0; }
+  __syncthreads();
+  int local = 0;
+  for (int i = tid; i < A; i += kTopkThreads) local += (kk[i] != 0ull);
+  for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((tid & 31) == 0 && local) atomicAdd(&s_valid, local);
+  __syncthreads();
+  const int valid = s_valid;
+  const int M = valid < K ? valid : K;
+  unsigned long long thr = 1ull;  // all valid keys
+  if (valid > K) {
+    if (tid == 0) { s_prefix = 0ull; s_remaining = K; }
+    __syncthreads();
+    for (int byte = 7; byte >= 0; --byte) {
+      for (int i = tid; i < 256; i += kTopkThreads) hist[i] = 0u;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = tid; i < A; i += kTopkThreads) {
+        const unsigned long long k = kk[i];
+        const bool match = (byte == 7) ? true : ((k >> (8 * (byte + 1))) == prefix);
+        if (match && k != 0ull) atomicAdd(&hist[(unsigned)(k >> (8 * byte)) & 255u], 1u);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int rem = s_remaining, d = 255;
+        for (; d > 0; --d) {
+          const int c = (int)hist[d];
+          if (c >= rem) break;
+          rem -= c;
+        }
+        s_remaining = rem;
+        s_prefix = (prefix << 8) | (unsigned long long)d;
+      }
+      __syncthreads();
+    }
+    thr = s_prefix;  // the K-th largest key (keys are unique: the low word is the anchor index)
+  }
+  for (int i = tid; i < Kpad; i += kTopkThreads) sk[i] = 0ull;
+  __syncthreads();
+  for (int i = tid; i < A; i += kTopkThreads) {
+    const unsigned long long k = kk[i];
+    if (k >= thr && k != 0ull) {
+      const int pos = atomicAdd(&s_fill, 1);
+      if (pos < Kpad) sk[pos] = k;
+    }
+  }
+  __syncthreads();
+  // bitonic sort, descending
+  for (int size = 2; size <= Kpad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (Kpad >> 1); i += kTopkThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = sk[lo], b = sk[hi];
+        if ((a < b) == desc) { sk[lo] = b; sk[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < M; i += kTopkThreads) {
+    const unsigned long long k = sk[i];
+    const unsigned int a = (unsigned int)(k & 0xFFFFFFFFull);
+    sorted_boxes[(size_t)n * Kpad + i] = boxes[(size_t)n * A + a];
+    sorted_scores[(size_t)n * Kpad + i] = orderable_float((uint32_t)(k >> 32));
+  }
+  if (tid == 0) counts[n] = M;
+}
+
+// ----------------------------------------------------------------------------------------
+// BoxIOU (util/math_functions.cpp:13-35), fp32, one rounding per operation.
+__device__ __forceinline__ float box_iou_ref(const float4 a, const float4 b, int mode) {
+  if (a.z <= 0.f || a.w <= 0.f || b.z <= 0.f || b.w <= 0.f) return 0.f;
+  const float tlx = (a.x < b.x) ? b.x : a.x;
+  const float tly = (a.y < b.y) ? b.y : a.y;
+  const float ax2 = a.x + a.z, bx2 = b.x + b.z, ay2 = a.y + a.w, by2 = b.y + b.w;
+  const float brx = (bx2 < ax2) ? bx2 : ax2;
+  const float bry = (by2 < ay2) ? by2 : ay2;
+  float over;
+  if (tlx >= brx || tly >= bry) over = 0.f;
+  else over = (brx - tlx) * (bry - tly);
+  float u;
+  if (mode == MSCNN_NMS_IOMU) {
+    const float a1 = a.z * a.w, a2 = b.z * b.w;
+    u = (a2 < a1) ? a2 : a1;
+  } else if (mode == MSCNN_NMS_IOFU) {
+    u = a.z * a.w;
+  } else {
+    u = a.z * a.w + b.z * b.w - over;
+  }
+  return over / u;
+}
+
+// mask[n][i][cb] bit t  <=>  IoU(box i, box cb*64+t) > thr  and  cb*64+t > i
+__global__ void nms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ counts,
+                                int Kpad, int words, float thr, int mode,
+                                unsigned long long* __restrict__ mask) {
+  const int n = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+  const int M = counts[n];
+  if (cb < rb || rb * 64 >= M || cb * 64 >= M) return;
+  __shared__ float4 cbox[64];
+  const int t = threadIdx.x;
+  const float4* bx = boxes + (size_t)n * Kpad;
+  if (cb * 64 + t < M) cbox[t] = bx[cb * 64 + t];
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i >= M) return;
+  const float4 me = bx[i];
+  const int ncol = min(64, M - cb * 64);
+  unsigned long long bits = 0ull;
+  const int start = (rb == cb) ? t + 1 : 0;
+  for (int c = start; c < ncol; ++c)
+    if (box_iou_ref(me, cbox[c], mode) > thr) bits |= (1ull << c);
+  mask[((size_t)n * Kpad + i) * words + cb] = bits;
+}
+
+// Greedy scan (nmsMax with greedy=true, box_output_layer.cpp:46-56).  One CTA per image.
+constexpr int kScanThreads = 128;
+__global__ void __launch_bounds__(kScanThreads)
+nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ counts, int Kpad,
+                int words, int max_post, int* __restrict__ keep_idx, int* __restrict__ keep_count) {
+  __shared__ unsigned long long remv[128];
+  __shared__ unsigned long long kept[128];
+  __shared__ unsigned long long diag[64];
+  __shared__ unsigned long long s_keptbits;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const int M = counts[n];
+  const int nb = (M + 63) / 64;
+  const unsigned long long* mk = mask + (size_t)n * Kpad * words;
+  for (int w = tid; w < 128; w += kScanThreads) { remv[w] = 0ull; kept[w] = 0ull; }
+  __syncthreads();
+  for (int b = 0; b < nb; ++b) {
+    const int rows = min(64, M - b * 64);
+    if (tid < rows) diag[tid] = mk[(size_t)(b * 64 + tid) * words + b];
+    __syncthreads();
+    if (tid == 0) {
+      unsigned long long cur = remv[b], kb = 0ull;
+      for (int i = 0; i < rows; ++i) {
+        if (!((cur >> i) & 1ull)) {
+          kb |= (1ull << i);
+          cur |= diag[i];
+        }
+      }
+      s_keptbits = kb;
+      kept[b] = kb;
+    }
+    __syncthreads();
+    const unsigned long long kb = s_keptbits;
+    for (int w = b + 1 + tid; w < nb; w += kScanThreads) {
+      unsigned long long acc = remv[w];
+      unsigned long long bits = kb;
+      while (bits) {
+        const int i = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        acc |= mk[(size_t)(b * 64 + i) * words + w];
+      }
+      remv[w] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    int r = 0;
+    for (int b = 0; b < nb; ++b) {
+      unsigned long long bits = kept[b];
+      while (bits) {
+        const int i = __ffsll((long long)bits) - 1;
+        bits &= bits - 1;
+        if (max_post <= 0 || r < max_post) keep_idx[(size_t)n * Kpad + r] = b * 64 + i;
+        ++r;
+      }
+    }
+    if (max_post > 0 && r > max_post) r = max_post;
+    keep_count[n] = r;
+  }
+}
+
+// Concatenate the kept boxes of all images in batch order: top[0] rows [img x1 y1 x1+w y1+h],
+// top[1] rows [... score] (box_output_layer.cpp:193-233); zero boxes -> dummy ROI / zero row.
+__global__ void box_finalize_kernel(const float4* __restrict__ boxes, const float* __restrict__ scores,
+                                    const int* __restrict__ keep_idx, const int* __restrict__ keep_count,
+                                    int N, int Kpad, float* __restrict__ rois, float* __restrict__ rois_score,
+                                    int* __restrict__ num_out) {
+  __shared__ int offs[1025];
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int n = 0; n < N; ++n) { offs[n] = acc; acc += keep_count[n]; }
+    offs[N] = acc;
+    num_out[0] = acc > 0 ? acc : 1;  // rows in the output blobs (dummy row when empty)
+    num_out[1] = acc;                // true number of proposals
+    for (int n = 0; n < N; ++n) num_out[2 + n] = keep_count[n];
+    if (acc == 0) {
+      rois[0] = 0.f; rois[1] = 1.f; rois[2] = 1.f; rois[3] = 10.f; rois[4] = 10.f;
+      if (rois_score) for (int k = 0; k < 6; ++k) rois_score[k] = 0.f;
+    }
+  }
+  __syncthreads();
+  for (int n = 0; n < N; ++n) {
+    const int cnt = offs[n + 1] - offs[n];
+    for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+      const int src = keep_idx[(size_t)n * Kpad + r];
+      const float4 b = boxes[(size_t)n * Kpad + src];
+      const size_t o = (size_t)(offs[n] + r);
+      const float x2 = b.x + b.z, y2 = b.y + b.w;
+      rois[o * 5 + 0] = (float)n; rois[o * 5 + 1] = b.x; rois[o * 5 + 2] = b.y;
+      rois[o * 5 + 3] = x2; rois[o * 5 + 4] = y2;
+      if (rois_score) {
+        rois_score[o * 6 + 0] = (float)n; rois_score[o * 6 + 1] = b.x; rois_score[o * 6 + 2] = b.y;
+        rois_score[o * 6 + 3] = x2; rois_score[o * 6 + 4] = y2;
+        rois_score[o * 6 + 5] = scores[(size_t)n * Kpad + src];
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// Final detections: the MATLAB post-process that follows the Caffe net in the reference
+// (examples/kitti_car/run_mscnn_detection.m:75-120 + utils/bbNms.m:112-126 nmsMax 'maxg').
+// MATLAB evaluates the decode in single precision (matcaffe returns single, and single op double
+// yields single) and the NMS in double on the converted singles; so do these kernels.
+struct DetectParams {
+  int num_cls, cls_id;  // cls_id is 1-based like the MATLAB script
+  float mean[4], stdv[4];
+  float proposal_thr, ratio_h, ratio_w, org_h, org_w;
+};
+
+// One CTA per image: decode every ROI of the image, rank by probability (MATLAB sort 'descend'
+// is stable: ties keep the lower row first), leave boxes sorted in `sboxes` / `sscores`.
+__global__ void __launch_bounds__(kTopkThreads)
+detect_decode_sort_kernel(const DetectParams p, const float* __restrict__ prop /*[R][6]*/,
+                          const float* __restrict__ cls /*[R][num_cls]*/,
+                          const float* __restrict__ bbox /*[R][4 num_cls]*/,
+                          const int* __restrict__ num_rois, int Kpad, float4* __restrict__ dboxes,
+                          float4* __restrict__ sboxes, float* __restrict__ sscores,
+                          int* __restrict__ counts) {
+  extern __shared__ unsigned long long sk[];
+  __shared__ int s_valid;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  int start = 0;
+  for (int m = 0; m < n; ++m) start += num_rois[2 + m];
+  int cnt = num_rois[2 + n];
+  if (cnt > Kpad) cnt = Kpad;
+  if (tid == 0) s_valid = 0;
+  for (int i = tid; i < Kpad; i += kTopkThreads) sk[i] = 0ull;
+  __syncthreads();
+  const int id = p.cls_id - 1;
+  for (int i = tid; i < cnt; i += kTopkThreads) {
+    const float* q = prop + (size_t)(start + i) * 6;
+    const float px = q[1], py = q[2], pw = q[3] - q[1], ph = q[4] - q[2], psc = q[5];
+    if (!(psc >= p.proposal_thr && pw != 0.f && ph != 0.f)) continue;
+    const float* c = cls + (size_t)(start + i) * p.num_cls;
+    const float* b = bbox + (size_t)(start + i) * 4 * p.num_cls + 4 * id;
+    const float dx = b[0] * p.stdv[0] + p.mean[0], dy = b[1] * p.stdv[1] + p.mean[1];
+    const float dw = b[2] * p.stdv[2] + p.mean[2], dh = b[3] * p.stdv[3] + p.mean[3];
+    float sum = 0.f, mine = 0.f;
+    for (int k = 0; k < p.num_cls; ++k) {
+      const float e = exp_ref(c[k]);
+      sum = sum + e;
+      if (k == id) mine = e;
+    }
+    const float prob = mine / sum;
+    const float cx = px + 0.5f * pw, cy = py + 0.5f * ph;
+    float tx = dx * pw + cx, ty = dy * ph + cy;
+    float tw = pw * exp_ref(dw), th = ph * exp_ref(dh);
+    tx = tx - tw / 2.f; ty = ty - th / 2.f;
+    tx = tx / p.ratio_w; tw = tw / p.ratio_w;
+    ty = ty / p.ratio_h; th = th / p.ratio_h;
+    tx = fmaxf(0.f, tx); ty = fmaxf(0.f, ty);
+    tw = fminf(tw, p.org_w - tx); th = fminf(th, p.org_h - ty);
+    if (prob != prob) continue;  // bbNms: kp = bbs(:,5) > -inf drops NaN
+    dboxes[(size_t)n * Kpad + i] = make_float4(tx, ty, tw, th);
+    sk[i] = ((unsigned long long)float_orderable(prob) << 32) | (unsigned int)(0xFFFFFFFFu - (unsigned)i);
+    atomicAdd(&s_valid, 1);
+  }
+  __syncthreads();
+  for (int size = 2; size <= Kpad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (Kpad >> 1); i += kTopkThreads) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = ((lo & size) == 0);
+        const unsigned long long a = sk[lo], b = sk[hi];
+        if ((a < b) == desc) { sk[lo] = b; sk[hi] = a; }
+      }
+      __syncthreads();
+    }
+  }
+  const int M = s_valid;
+  for (int i = tid; i < M; i += kTopkThreads) {
+    const unsigned long long k = sk[i];
+    const unsigned int src = 0xFFFFFFFFu - (unsigned int)(k & 0xFFFFFFFFull);
+    sboxes[(size_t)n * Kpad + i] = dboxes[(size_t)n * Kpad + src];
+    sscores[(size_t)n * Kpad + i] = orderable_float((uint32_t)(k >> 32));
+  }
+  if (tid == 0) counts[n] = M;
+}
+
+// bbNms.m:112-126 overlap test in double ('union' denominator).
+__device__ __forceinline__ bool bbnms_overlaps(const float4 a, const float4 b, double overlap) {
+  const double axs = a.x, axe = (double)a.x + (double)a.z, ays = a.y, aye = (double)a.y + (double)a.w;
+  const double bxs = b.x, bxe = (double)b.x + (double)b.z, bys = b.y, bye = (double)b.y + (double)b.w;
+  const double iw = fmin(axe, bxe) - fmax(axs, bxs);
+  if (iw <= 0) return false;
+  const double ih = fmin(aye, bye) - fmax(ays, bys);
+  if (ih <= 0) return false;
+  double o = iw * ih;
+  const double u = (double)a.z * (double)a.w + (double)b.z * (double)b.w - o;
+  o = o / u;
+  return o > overlap;
+}
+
+__global__ void bbnms_mask_kernel(const float4* __restrict__ boxes, const int* __restrict__ counts,
+                                  int Kpad, int words, double overlap,
+                                  unsigned long long* __restrict__ mask) {
+  const int n = blockIdx.z, rb = blockIdx.y, cb = blockIdx.x;
+  const int M = counts[n];
+  if (cb < rb || rb * 64 >= M || cb * 64 >= M) return;
+  __shared__ float4 cbox[64];
+  const int t = threadIdx.x;
+  const float4* bx = boxes + (size_t)n * Kpad;
+  if (cb * 64 + t < M) cbox[t] = bx[cb * 64 + t];
+  __syncthreads();
+  const int i = rb * 64 + t;
+  if (i >= M) return;
+  const float4 me = bx[i];
+  const int ncol = min(64, M - cb * 64);
+  unsigned long long bits = 0ull;
+  const int start = (rb == cb) ? t + 1 : 0;
+  for (int c = start; c < ncol; ++c)
+    if (bbnms_overlaps(me, cbox[c], overlap)) bits |= (1ull << c);
+  mask[((size_t)n * Kpad + i) * words + cb] = bits;
+}
+
+// dets[n][r] = [x y w h prob], r < det_counts[n], in kept (score-descending) order.
+__global__ void detect_write_kernel(const float4* __restrict__ sboxes, const float* __restrict__ sscores,
+                                    const int* __restrict__ keep_idx, const int* __restrict__ keep_count,
+                                    int Kpad, int cap, float* __restrict__ dets, int* __restrict__ det_counts) {
+  const int n = blockIdx.x;
+  int cnt = keep_count[n];
+  if (cnt > cap) cnt = cap;
+  for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+    const int src = keep_idx[(size_t)n * Kpad + r];
+    const float4 b = sboxes[(size_t)n * Kpad + src];
+    float* o = dets + ((size_t)n * cap + r) * 5;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = sscores[(size_t)n * Kpad + src];
+  }
+  if (threadIdx.x == 0) det_counts[n] = cnt;
+}
+
+static int next_pow2(int v) {
+  int p = 64;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+struct BoxWs {
+  size_t keys, boxes, sboxes, sscores, counts, mask, keep_idx, keep_count, total;
+};
+static BoxWs plan_ws(int N, int A, int Kpad) {
+  BoxWs w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+  w.keys = take((size_t)N * A * 8);
+  w.boxes = take((size_t)N * A * 16);
+  w.sboxes = take((size_t)N * Kpad * 16);
+  w.sscores = take((size_t)N * Kpad * 4);
+  w.counts = take((size_t)N * 4);
+  w.mask = take((size_t)N * Kpad * (Kpad / 64) * 8);
+  w.keep_idx = take((size_t)N * Kpad * 4);
+  w.keep_count = take((size_t)N * 4);
+  w.total = o;
+  return w;
+}
+
+}  // namespace mscnn
+
+using namespace mscnn;
+
+static int box_cfg_check(const mscnn_box_output_cfg* c, int N, int* A_out, int* Kpad_out) {
+  if (!c || N <= 0 || N > 1024 || c->num_scales <= 0 || c->num_scales > MSCNN_MAX_SCALES) return MSCNN_ERR_INVALID;
+  if (c->channels < 6) return MSCNN_ERR_INVALID;
+  // The reference treats max_nms_num == 0 as "no cap" (box_output_layer.cpp:176); the device
+  // path needs a bound for its shared-memory sort and supports caps up to 8192.
+  if (c->max_nms_num <= 0 || c->max_nms_num > 8192) return MSCNN_ERR_INVALID;
+  long A = 0;
+  for (int j = 0; j < c->num_scales; ++j) {
+    if (c->height[j] <= 0 || c->width[j] <= 0) return MSCNN_ERR_INVALID;
+    A += (long)c->height[j] * c->width[j];
+  }
+  if (A > (1l << 30)) return MSCNN_ERR_INVALID;
+  *A_out = (int)A;
+  *Kpad_out = next_pow2(c->max_nms_num);
+  return MSCNN_OK;
+}
+
+extern "C" int mscnn_box_output_workspace_bytes(const mscnn_box_output_cfg* cfg, int N, size_t* bytes) {
+  int A, Kpad;
+  const int rc = box_cfg_check(cfg, N, &A, &Kpad);
+  if (rc) return rc;
+  if (!bytes) return MSCNN_ERR_INVALID;
+  *bytes = plan_ws(N, A, Kpad).total;
+  return MSCNN_OK;
+}
+
+extern "C" int mscnn_box_output_forward(const mscnn_box_output_cfg* cfg, int N, const float* const* maps,
+                                        void* workspace, size_t workspace_bytes, float* proposals,
+                                        float* proposals_score, int* num_out, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  int A, Kpad;
+  int rc = box_cfg_check(cfg, N, &A, &Kpad);
+  if (rc) return rc;
+  if (!maps || !workspace || !proposals || !num_out) return MSCNN_ERR_INVALID;
+  const BoxWs w = plan_ws(N, A, Kpad);
+  if (workspace_bytes < w.total) return MSCNN_ERR_NOMEM;
+  char* ws = (char*)workspace;
+
+  DecodeParams p;
+  p.num_scales = cfg->num_scales;
+  p.channels = cfg->channels;
+  p.cls_num = cfg->channels - 4;
+  p.anchors_per_image = A;
+  p.fg_thr = cfg->fg_thr;
+  // box_output_layer.cpp:76-77, evaluated in fp32 like the reference (Dtype = float)
+  p.min_whr = logf(1.0f / cfg->field_whr);
+  p.max_whr = logf(cfg->field_whr);
+  p.min_xyr = -1.0f / cfg->field_xyr;
+  p.max_xyr = 1.0f / cfg->field_xyr;
+  p.min_size = cfg->min_size;
+  p.do_norm = cfg->do_bbox_norm;
+  for (int k = 0; k < 4; ++k) { p.mean[k] = cfg->bbox_mean[k]; p.stdv[k] = cfg->bbox_std[k]; }
+  int base = 0;
+  for (int j = 0; j < cfg->num_scales; ++j) {
+    DecodeScale& S = p.sc[j];
+    if (!maps[j]) return MSCNN_ERR_INVALID;
+    S.data = maps[j];
+    S.height = cfg->height[j];
+    S.width = cfg->width[j];
+    S.anchor_base = base;
+    S.field_w = cfg->field_w[j];
+    S.field_h = cfg->field_h[j];
+    S.rate = cfg->downsample_rate[j];
+    // int img_width = width*downsample_rates[j]  (int * float -> float -> int), :115
+    S.img_w = (float)(int)((float)S.width * S.rate);
+    S.img_h = (float)(int)((float)S.height * S.rate);
+    base += S.height * S.width;
+  }
+  unsigned long long* keys = (unsigned long long*)(ws + w.keys);
+  float4* boxes = (float4*)(ws + w.boxes);
+  float4* sboxes = (float4*)(ws + w.sboxes);
+  float* sscores = (float*)(ws + w.sscores);
+  int* counts = (int*)(ws + w.counts);
+  unsigned long long* mask = (unsigned long long*)(ws + w.mask);
+  int* keep_idx = (int*)(ws + w.keep_idx);
+  int* keep_count = (int*)(ws + w.keep_count);
+
+  box_decode_kernel<<<dim3((A + 255) / 256, N), 256, 0, stream>>>(p, N, keys, boxes);
+  const size_t topk_smem = (size_t)Kpad * 8;
+  cudaError_t e = cudaFuncSetAttribute(box_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)topk_smem);
+  if (e != cudaSuccess) return MSCNN_ERR_CUDA;
+  box_topk_kernel<<<N, kTopkThreads, topk_smem, stream>>>(keys, boxes, A, cfg->max_nms_num, Kpad, sboxes,
+                                                         sscores, counts);
+  const int words = Kpad / 64;
+  nms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words, cfg->iou_thr,
+                                                           cfg->nms_type, mask);
+  nms_scan_kernel<<<N, kScanThreads, 0, stream>>>(mask, counts, Kpad, words, cfg->max_post_nms_num,
+                                                  keep_idx, keep_count);
+  box_finalize_kernel<<<1, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, N, Kpad, proposals,
+                                             proposals_score, num_out);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mscnn_box_output_forward: %s\n", cudaGetErrorString(e));
+    return MSCNN_ERR_CUDA;
+  }
+  return MSCNN_OK;
+}
+
+// ------------------------------------------------------------------------- post-process
+namespace mscnn {
+struct DetWs {
+  size_t dboxes, sboxes, sscores, counts, mask, keep_idx, keep_count, total;
+};
+static DetWs plan_det_ws(int N, int Kpad) {
+  DetWs w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+  w.dboxes = take((size_t)N * Kpad * 16);
+  w.sboxes = take((size_t)N * Kpad * 16);
+  w.sscores = take((size_t)N * Kpad * 4);
+  w.counts = take((size_t)N * 4);
+  w.mask = take((size_t)N * Kpad * (Kpad / 64) * 8);
+  w.keep_idx = take((size_t)N * Kpad * 4);
+  w.keep_count = take((size_t)N * 4);
+  w.total = o;
+  return w;
+}
+}  // namespace mscnn
+
+static int det_cfg_check(const mscnn_detect_cfg* c, int N, int* Kpad) {
+  if (!c || N <= 0 || N > 1024 || c->num_cls < 2 || c->cls_id < 1 || c->cls_id > c->num_cls)
+    return MSCNN_ERR_INVALID;
+  if (c->max_rois_per_image <= 0 || c->max_rois_per_image > 8192) return MSCNN_ERR_INVALID;
+  *Kpad = next_pow2(c->max_rois_per_image);
+  return MSCNN_OK;
+}
+
+extern "C" int mscnn_detect_workspace_bytes(const mscnn_detect_cfg* cfg, int N, size_t* bytes) {
+  int Kpad;
+  const int rc = det_cfg_check(cfg, N, &Kpad);
+  if (rc) return rc;
+  if (!bytes) return MSCNN_ERR_INVALID;
+  *bytes = plan_det_ws(N, Kpad).total;
+  return MSCNN_OK;
+}
+
+extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
+                                        const float* cls_pred, const float* bbox_pred, const int* num_rois,
+                                        void* workspace, size_t workspace_bytes, float* dets,
+                                        int* det_counts, void* stream_v) {
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  int Kpad;
+  const int rc = det_cfg_check(cfg, N, &Kpad);
+  if (rc) return rc;
+  if (!proposals_score || !cls_pred || !bbox_pred || !num_rois || !workspace || !dets || !det_counts)
+    return MSCNN_ERR_INVALID;
+  const DetWs w = plan_det_ws(N, Kpad);
+  if (workspace_bytes < w.total) return MSCNN_ERR_NOMEM;
+  char* ws = (char*)workspace;
+  DetectParams p;
+  p.num_cls = cfg->num_cls;
+  p.cls_id = cfg->cls_id;
+  for (int k = 0; k < 4; ++k) { p.mean[k] = cfg->bbox_mean[k]; p.stdv[k] = cfg->bbox_std[k]; }
+  p.proposal_thr = cfg->proposal_thr;
+  p.ratio_h = cfg->ratio_h; p.ratio_w = cfg->ratio_w;
+  p.org_h = cfg->org_h; p.org_w = cfg->org_w;
+  float4* dboxes = (float4*)(ws + w.dboxes);
+  float4* sboxes = (float4*)(ws + w.sboxes);
+  float* sscores = (float*)(ws + w.sscores);
+  int* counts = (int*)(ws + w.counts);
+  unsigned long long* mask = (unsigned long long*)(ws + w.mask);
+  int* keep_idx = (int*)(ws + w.keep_idx);
+  int* keep_count = (int*)(ws + w.keep_count);
+  const size_t smem = (size_t)Kpad * 8;
+  cudaError_t e = cudaFuncSetAttribute(detect_decode_sort_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return MSCNN_ERR_CUDA;
+  detect_decode_sort_kernel<<<N, kTopkThreads, smem, stream>>>(p, proposals_score, cls_pred, bbox_pred,
+                                                              num_rois, Kpad, dboxes, sboxes, sscores, counts);
+  const int words = Kpad / 64;
+  bbnms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words,
+                                                             (double)cfg->nms_overlap, mask);
+  nms_scan_kernel<<<N, kScanThreads, 0, stream>>>(mask, counts, Kpad, words, 0, keep_idx, keep_count);
+  detect_write_kernel<<<N, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, Kpad,
+                                            cfg->max_rois_per_image, dets, det_counts);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mscnn_detect_postprocess: %s\n", cudaGetErrorString(e));
+    return MSCNN_ERR_CUDA;
+  }
+  return MSCNN_OK;
+}

@@ -1,0 +1,248 @@
+// HBM-bound plane kernels: Pooling, ROIPooling (+ fused Concat), depthwise 2x Deconvolution.
+// All work on NHWC bf16 planes with 16-byte (8-channel) vector accesses, so a warp touches
+// 512 contiguous bytes per pixel; values of split tensors are hi + lo evaluated in fp32.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "mscnn_b200.h"
+
+namespace mscnn {
+
+struct Vec8 {
+  float v[8];
+};
+
+__device__ __forceinline__ Vec8 load8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, size_t off) {
+  Vec8 r;
+  const uint4 a = *reinterpret_cast<const uint4*>(hi + off);
+  const __nv_bfloat162* ap = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r.v[2 * i] = __bfloat162float(ap[i].x);
+    r.v[2 * i + 1] = __bfloat162float(ap[i].y);
+  }
+  if (lo) {
+    const uint4 b = *reinterpret_cast<const uint4*>(lo + off);
+    const __nv_bfloat162* bp = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      r.v[2 * i] += __bfloat162float(bp[i].x);
+      r.v[2 * i + 1] += __bfloat162float(bp[i].y);
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const Vec8& x) {
+  uint4 a, b;
+  __nv_bfloat162* ap = reinterpret_cast<__nv_bfloat162*>(&a);
+  __nv_bfloat162* bp = reinterpret_cast<__nv_bfloat162*>(&b);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(x.v[2 * i]), h1 = __float2bfloat16_rn(x.v[2 * i + 1]);
+    ap[i] = __nv_bfloat162(h0, h1);
+    bp[i] = __nv_bfloat162(__float2bfloat16_rn(x.v[2 * i] - __bfloat162float(h0)),
+                           __float2bfloat16_rn(x.v[2 * i + 1] - __bfloat162float(h1)));
+  }
+  *reinterpret_cast<uint4*>(hi + off) = a;
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = b;
+}
+
+// ------------------------------------------------------------------------------- Pooling
+// PoolingLayer::Forward_cpu (src/caffe/layers/pooling_layer.cpp:128-220) with pad = 0:
+// output size in ceil mode (:90-93), windows clipped to the image, AVE divides by the clipped
+// window size (pad 0 => pool_size = (hend-hstart)*(wend-wstart), :196-203).
+__global__ void pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
+                            __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int N, int H,
+                            int W, int C, int Ho, int Wo, int k, int s, int mode) {
+  const int cg = C / 8;
+  const size_t total = (size_t)N * Ho * Wo * cg;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = idx % cg;
+    size_t r = idx / cg;
+    const int ow = r % Wo; r /= Wo;
+    const int oh = r % Ho;
+    const int n = r / Ho;
+    const int hs = oh * s, ws = ow * s;
+    const int he = min(hs + k, H), we = min(ws + k, W);
+    Vec8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = (mode == MSCNN_POOL_MAX) ? -3.402823466e+38f : 0.f;
+    for (int h = hs; h < he; ++h)
+      for (int w = ws; w < we; ++w) {
+        const Vec8 v = load8(xh, xl, ((size_t)(n * H + h) * W + w) * C + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (mode == MSCNN_POOL_MAX) acc.v[i] = (v.v[i] > acc.v[i]) ? v.v[i] : acc.v[i];
+          else acc.v[i] = acc.v[i] + v.v[i];
+        }
+      }
+    if (mode == MSCNN_POOL_AVE) {
+      const float sz = (float)((he - hs) * (we - ws));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc.v[i] = acc.v[i] / sz;
+    }
+    store8(yh, yl, ((size_t)(n * Ho + oh) * Wo + ow) * C + g * 8, acc);
+  }
+}
+
+// --------------------------------------------------------------------------- ROIPooling
+// ROIPoolingLayer::Forward_cpu (src/caffe/layers/roi_pooling_layer.cpp:49-139) including the
+// MS-CNN pad_ratio context extension (:66-72).  Output rows are written at channel offset
+// `c_off` of a [R][P][P][Cout_total] tensor, which fuses ConcatLayer (concat_layer.cpp:57-74).
+__global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
+                                const float* __restrict__ rois, int R, int N, int H, int W, int C,
+                                int PH, int PW, float scale, float pad_ratio,
+                                __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
+                                int Ctot, int c_off) {
+  const int cg = C / 8;
+  const size_t total = (size_t)R * PH * PW * cg;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = idx % cg;
+    size_t r = idx / cg;
+    const int pw = r % PW; r /= PW;
+    const int ph = r % PH;
+    const int roi = r / PH;
+    const float* q = rois + (size_t)roi * 5;
+    int b = (int)q[0];
+    b = min(max(b, 0), N - 1);  // the reference CHECKs the range (:63-64); never out of range here
+    const float pad_w = (q[3] - q[1] + 1.f) * pad_ratio;
+    const float pad_h = (q[4] - q[2] + 1.f) * pad_ratio;
+    const int sw = (int)roundf((q[1] - pad_w) * scale);
+    const int sh = (int)roundf((q[2] - pad_h) * scale);
+    const int ew = (int)roundf((q[3] + pad_w) * scale);
+    const int eh = (int)roundf((q[4] + pad_h) * scale);
+    const int roi_h = max(eh - sh + 1, 1), roi_w = max(ew - sw + 1, 1);
+    const float bin_h = (float)roi_h / (float)PH, bin_w = (float)roi_w / (float)PW;
+    int hstart = (int)floorf((float)ph * bin_h);
+    int wstart = (int)floorf((float)pw * bin_w);
+    int hend = (int)ceilf((float)(ph + 1) * bin_h);
+    int wend = (int)ceilf((float)(pw + 1) * bin_w);
+    hstart = min(max(hstart + sh, 0), H);
+    hend = min(max(hend + sh, 0), H);
+    wstart = min(max(wstart + sw, 0), W);
+    wend = min(max(wend + sw, 0), W);
+    const bool empty = (hend <= hstart) || (wend <= wstart);
+    Vec8 best;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) best.v[i] = empty ? 0.f : -3.402823466e+38f;
+    for (int h = hstart; h < hend; ++h)
+      for (int w = wstart; w < wend; ++w) {
+        const Vec8 v = load8(xh, xl, ((size_t)(b * H + h) * W + w) * C + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) best.v[i] = (v.v[i] > best.v[i]) ? v.v[i] : best.v[i];
+      }
+    store8(yh, yl, ((size_t)(roi * PH + ph) * PW + pw) * Ctot + c_off + g * 8, best);
+  }
+}
+
+// ------------------------------------------------------------ depthwise Deconvolution 2x
+// DeconvolutionLayer::Forward_cpu (src/caffe/layers/deconv_layer.cpp:25-40) for the shape the
+// MS-CNN "-2x" nets use: group == channels, kernel 4, stride 2, pad 1, no bias
+// (examples/kitti_car/mscnn-7s-576-2x/mscnn_deploy.prototxt:452-466):
+//   y[n, c, 2*iy - 1 + ky, 2*ix - 1 + kx] += x[n, c, iy, ix] * w[c, ky, kx]
+// Gather form: each output pixel has exactly 2 x 2 contributing taps.  Weights are read from
+// the layer blob (the bilinear filler is just the usual content, filler.hpp:248-258).
+__global__ void deconv2x_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
+                                const float* __restrict__ wt /*[C][4][4]*/, __nv_bfloat16* __restrict__ yh,
+                                __nv_bfloat16* __restrict__ yl, int N, int H, int W, int C, int Creal) {
+  const int cg = C / 8;
+  const int Ho = 2 * H, Wo = 2 * W;
+  const size_t total = (size_t)N * Ho * Wo * cg;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int g = idx % cg;
+    size_t r = idx / cg;
+    const int ox = r % Wo; r /= Wo;
+    const int oy = r % Ho;
+    const int n = r / Ho;
+    Vec8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+    // ky has the parity of oy+1; iy = (oy + 1 - ky) / 2.  The reference's col2im adds the
+    // kernel offsets in increasing (ky, kx) order (util/im2col.cpp:col2im_cpu), so do we.
+    for (int ky = (oy + 1) & 1; ky < 4; ky += 2) {
+      const int iy = (oy + 1 - ky) / 2;
+      if (oy + 1 - ky < 0 || iy >= H) continue;
+      for (int kx = (ox + 1) & 1; kx < 4; kx += 2) {
+        const int ix = (ox + 1 - kx) / 2;
+        if (ox + 1 - kx < 0 || ix >= W) continue;
+        const Vec8 v = load8(xh, xl, ((size_t)(n * H + iy) * W + ix) * C + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = g * 8 + i;
+          const float wv = (c < Creal) ? wt[(c * 4 + ky) * 4 + kx] : 0.f;
+          acc.v[i] = acc.v[i] + v.v[i] * wv;
+        }
+      }
+    }
+    store8(yh, yl, ((size_t)(n * Ho + oy) * Wo + ox) * C + g * 8, acc);
+  }
+}
+
+static int launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mscnn: %s launch failed: %s\n", what, cudaGetErrorString(e));
+    return MSCNN_ERR_CUDA;
+  }
+  return MSCNN_OK;
+}
+
+static int grid_for(size_t total, int threads) {
+  size_t b = (total + threads - 1) / threads;
+  const size_t cap = (size_t)mscnn_sm_count() * 16;  // 16 resident 256-thread CTAs per SM at most
+  if (b > cap) b = cap;
+  return (int)(b ? b : 1);
+}
+
+}  // namespace mscnn
+
+using namespace mscnn;
+
+extern "C" int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H,
+                                  int W, int C, int kernel, int stride, int mode, void* stream) {
+  if (!x_hi || !y_hi || N <= 0 || H <= 0 || W <= 0 || C % 8 || kernel <= 0 || stride <= 0)
+    return MSCNN_ERR_INVALID;
+  if ((x_lo == nullptr) != (y_lo == nullptr)) return MSCNN_ERR_INVALID;
+  if (mode != MSCNN_POOL_MAX && mode != MSCNN_POOL_AVE) return MSCNN_ERR_INVALID;
+  // pooling_layer.cpp:90-93 with pad 0
+  const int Ho = (H - kernel + stride - 1) / stride + 1;
+  const int Wo = (W - kernel + stride - 1) / stride + 1;
+  const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, N,
+      H, W, C, Ho, Wo, kernel, stride, mode);
+  return launch_check("pool");
+}
+
+extern "C" int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                      const float* rois, int R, int pooled_h, int pooled_w,
+                                      float spatial_scale, float pad_ratio, void* y_hi, void* y_lo,
+                                      int out_channels_total, int out_channel_offset, void* stream) {
+  if (!x_hi || !y_hi || !rois || N <= 0 || C % 8 || R < 0 || pooled_h <= 0 || pooled_w <= 0 ||
+      out_channels_total % 8 || out_channel_offset % 8 || out_channel_offset + C > out_channels_total)
+    return MSCNN_ERR_INVALID;
+  if (R == 0) return MSCNN_OK;
+  const size_t total = (size_t)R * pooled_h * pooled_w * (C / 8);
+  roi_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, rois, R, N, H, W, C, pooled_h, pooled_w,
+      spatial_scale, pad_ratio, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total,
+      out_channel_offset);
+  return launch_check("roi_pool");
+}
+
+extern "C" int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const float* w, void* y_hi,
+                                      void* y_lo, int N, int H, int W, int C, int Creal, void* stream) {
+  if (!x_hi || !y_hi || !w || N <= 0 || H <= 0 || W <= 0 || C % 8 || Creal > C) return MSCNN_ERR_INVALID;
+  if ((x_lo == nullptr) != (y_lo == nullptr)) return MSCNN_ERR_INVALID;
+  const size_t total = (size_t)N * 2 * H * 2 * W * (C / 8);
+  deconv2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, w, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
+      N, H, W, C, Creal);
+  return launch_check("deconv2x");
+}

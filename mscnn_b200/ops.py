@@ -140,3 +140,101 @@ def conv_forward(x: Planes, w: PackedWeights, pad: int, relu: bool, out_f32: boo
         out = Planes(y_hi, y_lo, w.cout)
     capi.check(capi.lib().mscnn_conv_forward(d, _stream()), "conv_forward")
     return out
+
+
+def pool_forward(x: Planes, kernel: int, stride: int, mode: int = capi.POOL_MAX) -> Planes:
+    n, h, w, c = x.hi.shape
+    ho = -(-(h - kernel) // stride) + 1
+    wo = -(-(w - kernel) // stride) + 1
+    y_hi = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=x.hi.device)
+    y_lo = torch.empty_like(y_hi) if x.lo is not None else None
+    capi.check(capi.lib().mscnn_pool_forward(capi.ptr(x.hi), capi.ptr(x.lo), capi.ptr(y_hi), capi.ptr(y_lo),
+                                             n, h, w, c, kernel, stride, mode, _stream()), "pool_forward")
+    return Planes(y_hi, y_lo, x.channels)
+
+
+def deconv2x_forward(x: Planes, w: torch.Tensor) -> Planes:
+    """w: fp32 [C][1][4][4] (group == channels, stride 2, pad 1, no bias)."""
+    n, h, wd, c = x.hi.shape
+    assert w.is_cuda and w.dtype == torch.float32 and w.is_contiguous() and tuple(w.shape[1:]) == (1, 4, 4)
+    y_hi = torch.empty((n, 2 * h, 2 * wd, c), dtype=torch.bfloat16, device=x.hi.device)
+    y_lo = torch.empty_like(y_hi) if x.lo is not None else None
+    capi.check(capi.lib().mscnn_deconv2x_forward(capi.ptr(x.hi), capi.ptr(x.lo), capi.ptr(w), capi.ptr(y_hi),
+                                                 capi.ptr(y_lo), n, h, wd, c, w.shape[0], _stream()),
+               "deconv2x_forward")
+    return Planes(y_hi, y_lo, x.channels)
+
+
+def make_box_cfg(maps_shapes, field_w, field_h, rate, fg_thr, iou_thr, nms_type="IOU", field_whr=2.0,
+                 field_xyr=2.0, min_size=15.0, max_nms_num=2000, max_post_nms_num=0, bbox_mean=None,
+                 bbox_std=None) -> capi.BoxOutputCfg:
+    """maps_shapes: [(C, H, W)] per bottom, in bottom order (BoxOutputParameter, caffe.proto:1315-1329)."""
+    cfg = capi.BoxOutputCfg()
+    cfg.num_scales = len(maps_shapes)
+    cfg.channels = maps_shapes[0][0]
+    for j, (c, h, w) in enumerate(maps_shapes):
+        assert c == cfg.channels
+        cfg.height[j], cfg.width[j] = h, w
+        cfg.field_w[j], cfg.field_h[j], cfg.downsample_rate[j] = field_w[j], field_h[j], rate[j]
+    cfg.fg_thr, cfg.iou_thr = fg_thr, iou_thr
+    cfg.nms_type = {"IOU": capi.NMS_IOU, "IOMU": capi.NMS_IOMU, "IOFU": capi.NMS_IOFU}.get(nms_type, capi.NMS_IOU)
+    cfg.field_whr, cfg.field_xyr, cfg.min_size = field_whr, field_xyr, min_size
+    cfg.max_nms_num, cfg.max_post_nms_num = max_nms_num, max_post_nms_num
+    cfg.do_bbox_norm = int(bool(bbox_mean) and bool(bbox_std))
+    for k in range(4):
+        cfg.bbox_mean[k] = bbox_mean[k] if cfg.do_bbox_norm else 0.0
+        cfg.bbox_std[k] = bbox_std[k] if cfg.do_bbox_norm else 1.0
+    return cfg
+
+
+def box_output_forward(cfg: capi.BoxOutputCfg, maps: list[torch.Tensor]):
+    """maps: fp32 NCHW score/delta maps.  Returns (proposals[cap,5], proposals_score[cap,6],
+    num_out int32[2+N]) device tensors; rows beyond num_out[0] are undefined."""
+    import ctypes as C
+    n = maps[0].shape[0]
+    dev = maps[0].device
+    for m in maps:
+        assert m.is_cuda and m.dtype == torch.float32 and m.is_contiguous() and m.shape[0] == n
+    nbytes = C.c_size_t(0)
+    capi.check(capi.lib().mscnn_box_output_workspace_bytes(cfg, n, C.byref(nbytes)), "box_output_workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    cap = max(n * cfg.max_nms_num, 1)
+    rois = torch.empty((cap, 5), dtype=torch.float32, device=dev)
+    rois_score = torch.empty((cap, 6), dtype=torch.float32, device=dev)
+    num_out = torch.zeros(2 + n, dtype=torch.int32, device=dev)
+    ptrs = (C.c_void_p * len(maps))(*[m.data_ptr() for m in maps])
+    capi.check(capi.lib().mscnn_box_output_forward(cfg, n, ptrs, capi.ptr(ws), nbytes.value, capi.ptr(rois),
+                                                   capi.ptr(rois_score), capi.ptr(num_out), _stream()),
+               "box_output_forward")
+    return rois, rois_score, num_out
+
+
+def roi_pool_forward(x: Planes, rois: torch.Tensor, num_rois: int, pooled: int, scale: float,
+                     pad_ratio: float, out: Planes | None = None, channel_offset: int = 0,
+                     out_channels: int | None = None) -> Planes:
+    n, h, w, c = x.hi.shape
+    ctot = out_channels or c
+    if out is None:
+        y_hi = torch.zeros((num_rois, pooled, pooled, ctot), dtype=torch.bfloat16, device=x.hi.device)
+        y_lo = torch.zeros_like(y_hi) if x.lo is not None else None
+        out = Planes(y_hi, y_lo, ctot)
+    capi.check(capi.lib().mscnn_roi_pool_forward(capi.ptr(x.hi), capi.ptr(x.lo), n, h, w, c, capi.ptr(rois),
+                                                 num_rois, pooled, pooled, scale, pad_ratio, capi.ptr(out.hi),
+                                                 capi.ptr(out.lo), ctot, channel_offset, _stream()),
+               "roi_pool_forward")
+    return out
+
+
+def detect_postprocess(cfg: capi.DetectCfg, n: int, proposals_score, cls_pred, bbox_pred, num_out):
+    import ctypes as C
+    dev = proposals_score.device
+    nbytes = C.c_size_t(0)
+    capi.check(capi.lib().mscnn_detect_workspace_bytes(cfg, n, C.byref(nbytes)), "detect_workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    dets = torch.zeros((n, cfg.max_rois_per_image, 5), dtype=torch.float32, device=dev)
+    counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    capi.check(capi.lib().mscnn_detect_postprocess(cfg, n, capi.ptr(proposals_score), capi.ptr(cls_pred),
+                                                   capi.ptr(bbox_pred), capi.ptr(num_out), capi.ptr(ws),
+                                                   nbytes.value, capi.ptr(dets), capi.ptr(counts), _stream()),
+               "detect_postprocess")
+    return dets, counts
