@@ -32,6 +32,14 @@
 extern "C" {
 #endif
 
+/* Only the C ABI is exported from libmscnn_b200.so (the library is built with hidden visibility
+ * so that its internal C++ symbols cannot collide with another Caffe in the same process). */
+#if defined(__GNUC__)
+#define MSCNN_API __attribute__((visibility("default")))
+#else
+#define MSCNN_API
+#endif
+
 #define MSCNN_OK 0
 #define MSCNN_ERR_INVALID (-1) /* bad argument / unsupported shape */
 #define MSCNN_ERR_CUDA (-2)    /* CUDA runtime or driver error (message on stderr) */
@@ -50,8 +58,8 @@ extern "C" {
 #define MSCNN_MAX_SCALES 16
 
 /* library / device ------------------------------------------------------------------ */
-const char* mscnn_version(void);
-int mscnn_sm_count(void);
+MSCNN_API const char* mscnn_version(void);
+MSCNN_API int mscnn_sm_count(void);
 
 /* ------------------------------------------------------------------------------------
  * Convolution (stride 1) / InnerProduct with fused bias and optional ReLU.
@@ -79,26 +87,26 @@ typedef struct mscnn_conv_desc {
   void* y_lo; /* may be NULL even when x_lo is set (bf16-only output) */
   float* y_f32;
 } mscnn_conv_desc;
-int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream);
+MSCNN_API int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream);
 
 /* Weight packing (done once at load time; replaces nothing in the reference -- Caffe keeps
  * [Cout][Cin][KH][KW] fp32, blob layout base_conv_layer.cpp:135-142).
  *   conv: w_f32 [Cout][Cin][KH][KW] -> planes [Cout_pad][KH][KW][Cin_pad], zero padded.
  *   fc  : w_f32 [Nout][C*H*W] (Caffe flattening c*H*W + h*W + w, inner_product_layer.cpp:32-48)
  *         -> planes [Nout_pad][(h*W + w)*Cpad + c], the NHWC flattening of the bottom. */
-int mscnn_pack_conv_weights(const float* w_f32, void* w_hi, void* w_lo, int Cout, int Cin, int KH,
+MSCNN_API int mscnn_pack_conv_weights(const float* w_f32, void* w_hi, void* w_lo, int Cout, int Cin, int KH,
                             int KW, int Cout_pad, int Cin_pad, void* stream);
-int mscnn_pack_fc_weights(const float* w_f32, void* w_hi, void* w_lo, int Nout, int C, int H, int W,
+MSCNN_API int mscnn_pack_fc_weights(const float* w_f32, void* w_hi, void* w_lo, int Nout, int C, int H, int W,
                           int Nout_pad, int Cpad, void* stream);
 
 /* Layout converters between Caffe blobs (NCHW fp32, blob.hpp:153-164) and planes. */
-int mscnn_nchw_f32_to_planes(const float* x, void* hi, void* lo, int N, int C, int H, int W,
+MSCNN_API int mscnn_nchw_f32_to_planes(const float* x, void* hi, void* lo, int N, int C, int H, int W,
                              int Cpad, void* stream);
-int mscnn_planes_to_nchw_f32(const void* hi, const void* lo, float* y, int N, int C, int H, int W,
+MSCNN_API int mscnn_planes_to_nchw_f32(const void* hi, const void* lo, float* y, int N, int C, int H, int W,
                              int Cpad, void* stream);
 /* conv1_1 operand: 3x3 / pad 1 patches of a 3-channel NCHW fp32 image as 64-channel planes,
  * channel k = c*9 + dy*3 + dx for k < 27 (Caffe's own weight order), zero above. */
-int mscnn_im2col3x3_c3_to_planes(const float* x, void* hi, void* lo, int N, int H, int W,
+MSCNN_API int mscnn_im2col3x3_c3_to_planes(const float* x, void* hi, void* lo, int N, int H, int W,
                                  void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -106,14 +114,22 @@ int mscnn_im2col3x3_c3_to_planes(const float* x, void* hi, void* lo, int N, int 
  * (src/caffe/layers/pooling_layer.cu:158-190; shape pooling_layer.cpp:79-123).
  *   x planes [N][H][W][C] (C % 8 == 0) -> y planes [N][Ho][Wo][C],
  *   Ho = ceil((H - kernel) / stride) + 1.  mode = MSCNN_POOL_MAX | MSCNN_POOL_AVE. */
-int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H, int W,
+MSCNN_API int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H, int W,
                        int C, int kernel, int stride, int mode, void* stream);
+
+/* Stand-alone ReLU (in place) and channel Concat for planes / fp32 blobs.  mscnn_b200's Net fuses
+ * ReLU into the producing convolution and Concat into ROIPooling; these serve unfused use.
+ * Replace ReLULayer::Forward_gpu (relu_layer.cu:9-26) and ConcatLayer::Forward_gpu
+ * (concat_layer.cu:9-46).  count = elements per plane (multiple of 8). */
+MSCNN_API int mscnn_relu_planes(void* hi, void* lo, size_t count, void* stream);
+MSCNN_API int mscnn_relu_f32(float* x, size_t count, void* stream);
+MSCNN_API int mscnn_concat_planes(const void* x, void* y, size_t pixels, int C, int Ctot, int offset, void* stream);
 
 /* Depthwise transposed convolution, kernel 4 / stride 2 / pad 1 / group == channels / no bias:
  * the "conv4_3_2x" layer of the -2x nets.  Replaces DeconvolutionLayer::Forward_gpu
  * (src/caffe/layers/deconv_layer.cu) for that shape.  w: fp32 [Creal][1][4][4] (layer blob 0).
  *   x planes [N][H][W][C] -> y planes [N][2H][2W][C]. */
-int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo,
+MSCNN_API int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const float* w, void* y_hi, void* y_lo,
                            int N, int H, int W, int C, int Creal, void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -140,8 +156,8 @@ typedef struct mscnn_box_output_cfg {
   int do_bbox_norm;
   float bbox_mean[4], bbox_std[4];
 } mscnn_box_output_cfg;
-int mscnn_box_output_workspace_bytes(const mscnn_box_output_cfg* cfg, int N, size_t* bytes);
-int mscnn_box_output_forward(const mscnn_box_output_cfg* cfg, int N, const float* const* maps /*host array*/,
+MSCNN_API int mscnn_box_output_workspace_bytes(const mscnn_box_output_cfg* cfg, int N, size_t* bytes);
+MSCNN_API int mscnn_box_output_forward(const mscnn_box_output_cfg* cfg, int N, const float* const* maps /*host array*/,
                              void* workspace, size_t workspace_bytes, float* proposals,
                              float* proposals_score, int* num_out, void* stream);
 
@@ -152,7 +168,7 @@ int mscnn_box_output_forward(const mscnn_box_output_cfg* cfg, int N, const float
  * ConcatLayer::Forward_gpu (concat_layer.cu:28-46).
  *   x planes [N][H][W][C]; rois fp32 [R][5] = [img x1 y1 x2 y2];
  *   y planes [R][pooled_h][pooled_w][out_channels_total], channels [offset, offset + C). */
-int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+MSCNN_API int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
                            const float* rois, int R, int pooled_h, int pooled_w, float spatial_scale,
                            float pad_ratio, void* y_hi, void* y_lo, int out_channels_total,
                            int out_channel_offset, void* stream);
@@ -174,11 +190,51 @@ typedef struct mscnn_detect_cfg {
   float org_h, org_w;
   int max_rois_per_image; /* 1..8192 */
 } mscnn_detect_cfg;
-int mscnn_detect_workspace_bytes(const mscnn_detect_cfg* cfg, int N, size_t* bytes);
-int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
+MSCNN_API int mscnn_detect_workspace_bytes(const mscnn_detect_cfg* cfg, int N, size_t* bytes);
+MSCNN_API int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
                              const float* cls_pred, const float* bbox_pred, const int* num_rois,
                              void* workspace, size_t workspace_bytes, float* dets, int* det_counts,
                              void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Net facade: caffe::Net<float> of the Caffe-API mirror (mscnn_b200/csrc/caffe_api) for hosts that
+ * cannot include C++ headers.  Mirrors what matcaffe / pycaffe expose of Net
+ * (/root/reference/matlab/+caffe/private/caffe_.cpp, python/caffe/_caffe.cpp):
+ * create from a deploy prototxt (TEST phase), copy parameters by layer name, set inputs, forward,
+ * read any blob in Caffe layout (NCHW fp32).  C++ hosts use caffe::Net directly.
+ * Structural errors (bad prototxt graph, shape mismatch) abort like Caffe's CHECKs. */
+MSCNN_API int mscnn_set_device(int device);
+MSCNN_API int mscnn_set_stream(void* stream);      /* stream used by all layers of this thread's context */
+MSCNN_API int mscnn_set_precision(int bf16);       /* 0: fp32-faithful split-bf16 (default), 1: plain bf16 */
+MSCNN_API int mscnn_get_precision(void);
+MSCNN_API void* mscnn_net_create(const char* prototxt_path_or_text, int is_path);
+MSCNN_API void mscnn_net_destroy(void* net);
+MSCNN_API int mscnn_net_num_layers(void* net);
+MSCNN_API const char* mscnn_net_layer_name(void* net, int i);
+MSCNN_API const char* mscnn_net_layer_type(void* net, int i);
+MSCNN_API int mscnn_net_layer_param_string(void* net, int i, char* buf, int cap);
+MSCNN_API int mscnn_net_num_params(void* net, const char* layer);
+MSCNN_API int mscnn_net_param_shape(void* net, const char* layer, int idx, int* shape4); /* returns #axes */
+MSCNN_API int mscnn_net_set_param(void* net, const char* layer, int idx, const float* host, long count);
+MSCNN_API int mscnn_net_copy_trained(void* net, const char* caffemodel_path); /* Net::CopyTrainedLayersFrom */
+MSCNN_API int mscnn_net_num_blobs(void* net);
+MSCNN_API const char* mscnn_net_blob_name(void* net, int i);
+MSCNN_API int mscnn_net_num_inputs(void* net);
+MSCNN_API int mscnn_net_num_outputs(void* net);
+MSCNN_API const char* mscnn_net_input_name(void* net, int i);
+MSCNN_API const char* mscnn_net_output_name(void* net, int i);
+MSCNN_API int mscnn_net_blob_shape(void* net, const char* blob, int* shape4); /* returns #axes */
+MSCNN_API int mscnn_net_reshape_blob(void* net, const char* blob, int n, int c, int h, int w);
+MSCNN_API int mscnn_net_reshape(void* net);
+MSCNN_API int mscnn_net_set_blob(void* net, const char* blob, const float* host, long count);       /* async H2D */
+MSCNN_API int mscnn_net_set_blob_device(void* net, const char* blob, const float* dev, long count); /* async D2D */
+MSCNN_API int mscnn_net_get_blob(void* net, const char* blob, float* host, long count);             /* D2H + sync */
+MSCNN_API const float* mscnn_net_blob_device(void* net, const char* blob);
+MSCNN_API int mscnn_net_forward(void* net, int from_layer, int to_layer); /* inclusive; to < 0 = last */
+MSCNN_API int mscnn_net_set_layer_timing(void* net, int on);
+MSCNN_API int mscnn_net_layer_times(void* net, float* ms);                 /* ms per layer, last forward */
+MSCNN_API int mscnn_net_num_proposals(void* net, int image);               /* image < 0: whole batch */
+MSCNN_API int mscnn_net_detect(void* net, const mscnn_detect_cfg* cfg, float* dets_dev, int* det_counts_dev);
 
 #ifdef __cplusplus
 }

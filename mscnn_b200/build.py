@@ -22,12 +22,12 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
+    "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function,-fvisibility=hidden,-fno-gnu-unique",
     "--expt-relaxed-constexpr",
     # decode / IoU arithmetic must round exactly like the reference's scalar CPU code:
     # no FMA contraction anywhere unless a kernel asks for it explicitly with __fmaf_rn.
     "-fmad=false",
-    "-I", str(ROOT / "include"), "-I", str(CSRC),
+    "-I", str(ROOT / "include"), "-I", str(CSRC), "-I", str(CSRC / "caffe_api"), "-I", str(CSRC / "proto_shared"),
 ]
 
 
@@ -37,7 +37,8 @@ def _sources() -> list[Path]:
 
 def _headers() -> list[Path]:
     return sorted(list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.hpp"))
-                  + list((CSRC / "caffe").glob("**/*.hpp")) + list((ROOT / "include").glob("*.h")))
+                  + list((CSRC / "caffe_api").glob("**/*.hpp")) + list((CSRC / "proto_shared").glob("**/*.h*"))
+                  + list((ROOT / "include").glob("*.h")))
 
 
 def _digest(paths: list[Path], extra: str) -> str:
@@ -74,7 +75,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if rebuilt or force or not LIB.exists():
         # static cudart (nvcc default): the library carries its own runtime and shares the
         # primary context with torch, so torch device pointers / streams are usable as-is.
-        cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs)]
+        cmd = [NVCC, "-shared", "-Xlinker", "-Bsymbolic", "-o", str(LIB), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -1,0 +1,239 @@
+// The eleven layer types the MS-CNN deploy nets instantiate (census: SURVEY.md section 2), as
+// caffe::Layer<Dtype> subclasses whose Forward_gpu calls the C ABI in include/mscnn_b200.h.
+// Class names, type() strings, blob layouts and parameter semantics are the reference's
+// (/root/reference/include/caffe/layers/*.hpp); the per-layer headers next to this file
+// (conv_layer.hpp, ...) only include this one so that existing #include lines keep working.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "caffe/blob.hpp"
+#include "caffe/layer.hpp"
+#include "caffe/proto/caffe.pb.h"
+
+namespace caffe {
+
+// Fill a parameter blob according to a FillerParameter (include/caffe/filler.hpp).  Supported:
+// constant, gaussian, bilinear (the only ones the MS-CNN prototxts name); anything else aborts.
+void FillBlob(const FillerParameter& filler, Blob<float>* blob);
+
+// Device copies of packed weights (planes) owned by Convolution / InnerProduct layers.
+struct PackedParam {
+  PlaneStore w;          // [Cout_pad][KH][KW][Cin_pad] bf16 hi (+lo)
+  float* bias = nullptr; // [Cout_pad]
+  int cout_pad = 0, cin_pad = 0;
+  unsigned long w_version = ~0ul, b_version = ~0ul;
+  bool split = false;
+  long key = -1;         // layout key (fc: bottom C*H*W arrangement)
+  ~PackedParam();
+};
+
+/// InputLayer: /root/reference/src/caffe/layers/input_layer.cpp:8-22
+template <typename Dtype>
+class InputLayer : public Layer<Dtype> {
+ public:
+  explicit InputLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {}
+  virtual inline const char* type() const { return "Input"; }
+  virtual inline int ExactNumBottomBlobs() const { return 0; }
+  virtual inline int MinTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {}
+};
+
+/// ConvolutionLayer: conv_layer.cpp:8-40 / base_conv_layer.cpp:15-254 (stride 1, group 1, dilation 1:
+/// every Convolution in the shipped deploy nets).  blobs_[0] = [Cout, Cin, kh, kw], blobs_[1] = [Cout].
+template <typename Dtype>
+class ConvolutionLayer : public Layer<Dtype> {
+ public:
+  explicit ConvolutionLayer(const LayerParameter& param) : Layer<Dtype>(param), fuse_relu_(false) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "Convolution"; }
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+  // mscnn_b200 extension: fold the in-place ReLU that follows into the epilogue (set by Net).
+  void set_fuse_relu(bool f) { fuse_relu_ = f; }
+  bool fuse_relu() const { return fuse_relu_; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  int num_output_, channels_, kernel_h_, kernel_w_, pad_h_, pad_w_;
+  bool bias_term_, fuse_relu_;
+  PackedParam packed_;
+  PlaneStore patches_;  // conv1_1: 27-tap patch planes
+};
+
+/// DeconvolutionLayer: deconv_layer.cpp:8-40, restricted to the depthwise 4/2/1 bilinear-upsampling
+/// shape of the "-2x" nets.
+template <typename Dtype>
+class DeconvolutionLayer : public Layer<Dtype> {
+ public:
+  explicit DeconvolutionLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "Deconvolution"; }
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  int channels_;
+};
+
+/// ReLULayer: relu_layer.cpp:9-19 (negative_slope 0), in place.
+template <typename Dtype>
+class ReLULayer : public Layer<Dtype> {
+ public:
+  explicit ReLULayer(const LayerParameter& param) : Layer<Dtype>(param), fused_(false) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+    top[0]->ReshapeLike(*bottom[0]);
+  }
+  virtual inline const char* type() const { return "ReLU"; }
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+  void set_fused(bool f) { fused_ = f; }   // producer already applied it
+  bool fused() const { return fused_; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  bool fused_;
+};
+
+/// PoolingLayer: pooling_layer.cpp:16-220 (MAX / AVE, pad 0, ceil-mode output size).
+template <typename Dtype>
+class PoolingLayer : public Layer<Dtype> {
+ public:
+  explicit PoolingLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "Pooling"; }
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int MinTopBlobs() const { return 1; }
+  virtual inline int MaxTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  int kernel_, stride_, mode_, pooled_h_, pooled_w_;
+};
+
+/// SplitLayer: split_layer.cpp:9-31 (forward = share data).
+template <typename Dtype>
+class SplitLayer : public Layer<Dtype> {
+ public:
+  explicit SplitLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "Split"; }
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int MinTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+};
+
+/// ConcatLayer: concat_layer.cpp:11-74, channel axis.
+template <typename Dtype>
+class ConcatLayer : public Layer<Dtype> {
+ public:
+  explicit ConcatLayer(const LayerParameter& param) : Layer<Dtype>(param), fused_(false) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "Concat"; }
+  virtual inline int MinBottomBlobs() const { return 1; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+  void set_fused(bool f) { fused_ = f; }   // the producers write straight into top[0]
+  bool fused() const { return fused_; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  bool fused_;
+};
+
+/// InnerProductLayer: inner_product_layer.cpp:10-97 (axis 1, no transpose).
+/// blobs_[0] = [N_out, K] with K in the bottom's NCHW flattening, blobs_[1] = [N_out].
+template <typename Dtype>
+class InnerProductLayer : public Layer<Dtype> {
+ public:
+  explicit InnerProductLayer(const LayerParameter& param) : Layer<Dtype>(param), fuse_relu_(false) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "InnerProduct"; }
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+  void set_fuse_relu(bool f) { fuse_relu_ = f; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  int M_, K_, N_;
+  bool bias_term_, fuse_relu_;
+  PackedParam packed_;
+};
+
+/// DropoutLayer: dropout_layer.cpp:31-46 -- TEST phase is the identity.
+template <typename Dtype>
+class DropoutLayer : public Layer<Dtype> {
+ public:
+  explicit DropoutLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+    if (top[0] != bottom[0]) top[0]->ReshapeLike(*bottom[0]);
+  }
+  virtual inline const char* type() const { return "Dropout"; }
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+};
+
+/// BoxOutputLayer: box_output_layer.cpp:19-234.  top[0] = [R,5,1,1] ROIs, top[1] = [R,6,1,1] with score.
+/// Unlike the reference (CPU only) this runs on the device; one small D2H copy of the row count
+/// is needed because the Caffe API exposes R as the blobs' shape.
+template <typename Dtype>
+class BoxOutputLayer : public Layer<Dtype> {
+ public:
+  explicit BoxOutputLayer(const LayerParameter& param)
+      : Layer<Dtype>(param), workspace_(nullptr), workspace_bytes_(0), num_out_dev_(nullptr),
+        num_out_host_(nullptr), num_out_cap_(0) {}
+  virtual ~BoxOutputLayer();
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "BoxOutput"; }
+  virtual inline int MinBottomBlobs() const { return 1; }
+  virtual inline int MinTopBlobs() const { return 1; }
+  virtual inline int MaxTopBlobs() const { return 2; }
+  // mscnn_b200 extensions: results of the last Forward
+  const int* num_out_device() const { return num_out_dev_; }   // int[2+N], see mscnn_box_output_forward
+  int num_proposals() const { return num_out_host_ ? num_out_host_[1] : 0; }
+  int image_proposals(int n) const { return num_out_host_[2 + n]; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  mscnn_box_output_cfg cfg_;
+  bool output_proposal_with_score_;
+  void* workspace_;
+  size_t workspace_bytes_;
+  int* num_out_dev_;
+  int* num_out_host_;
+  int num_out_cap_;
+  Blob<Dtype> scratch_score_;
+};
+
+/// ROIPoolingLayer: roi_pooling_layer.cpp:22-139 with the MS-CNN pad_ratio extension.
+template <typename Dtype>
+class ROIPoolingLayer : public Layer<Dtype> {
+ public:
+  explicit ROIPoolingLayer(const LayerParameter& param)
+      : Layer<Dtype>(param), concat_top_(nullptr), concat_offset_(0), concat_channels_(0) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "ROIPooling"; }
+  virtual inline int MinBottomBlobs() const { return 2; }
+  virtual inline int MaxBottomBlobs() const { return 2; }
+  virtual inline int MinTopBlobs() const { return 1; }
+  virtual inline int MaxTopBlobs() const { return 1; }
+  // mscnn_b200 extension (set by Net): write into `target` (the Concat top) at a channel offset.
+  void set_concat_target(Blob<Dtype>* target, int channel_offset, int total_channels) {
+    concat_top_ = target; concat_offset_ = channel_offset; concat_channels_ = total_channels;
+  }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  int channels_, height_, width_, pooled_height_, pooled_width_;
+  float spatial_scale_, pad_ratio_;
+  Blob<Dtype>* concat_top_;
+  int concat_offset_, concat_channels_;
+};
+
+}  // namespace caffe

@@ -184,6 +184,41 @@ __global__ void deconv2x_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
   }
 }
 
+// ------------------------------------------------------------------ stand-alone ReLU / Concat
+// Used only when a ReLU / Concat layer is run unfused (outside mscnn_b200's Net, which folds
+// ReLU into the producing convolution and Concat into ROIPooling).
+// relu(hi + lo): |lo| <= ulp(hi)/2, so the sign of the sum is the sign of hi.
+__global__ void relu_planes_kernel(__nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, size_t n8) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    uint4 a = reinterpret_cast<uint4*>(hi)[i];
+    uint4 b = lo ? reinterpret_cast<uint4*>(lo)[i] : make_uint4(0, 0, 0, 0);
+    uint32_t* ap = reinterpret_cast<uint32_t*>(&a);
+    uint32_t* bp = reinterpret_cast<uint32_t*>(&b);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (ap[k] & 0x00008000u) { ap[k] &= 0xFFFF0000u; bp[k] &= 0xFFFF0000u; }   // low element negative
+      if (ap[k] & 0x80000000u) { ap[k] &= 0x0000FFFFu; bp[k] &= 0x0000FFFFu; }   // high element negative
+    }
+    reinterpret_cast<uint4*>(hi)[i] = a;
+    if (lo) reinterpret_cast<uint4*>(lo)[i] = b;
+  }
+}
+__global__ void relu_f32_kernel(float* __restrict__ x, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = fmaxf(x[i], 0.f);
+}
+// y[p][off .. off+C) = x[p][0 .. C) for every pixel p (channel concat of NHWC planes)
+__global__ void concat_planes_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                     size_t pixels, int C, int Ctot, int off) {
+  const int cg = C / 8;
+  const size_t total = pixels * cg;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t p = i / cg;
+    const int g = i % cg;
+    *reinterpret_cast<uint4*>(y + p * Ctot + off + g * 8) = *reinterpret_cast<const uint4*>(x + p * C + g * 8);
+  }
+}
+
 static int launch_check(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -245,4 +280,28 @@ extern "C" int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const 
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, w, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
       N, H, W, C, Creal);
   return launch_check("deconv2x");
+}
+
+extern "C" int mscnn_relu_planes(void* hi, void* lo, size_t count, void* stream) {
+  if (!hi || count % 8) return MSCNN_ERR_INVALID;
+  if (count == 0) return MSCNN_OK;
+  relu_planes_kernel<<<grid_for(count / 8, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)hi,
+                                                                                 (__nv_bfloat16*)lo, count / 8);
+  return launch_check("relu_planes");
+}
+
+extern "C" int mscnn_relu_f32(float* x, size_t count, void* stream) {
+  if (!x) return MSCNN_ERR_INVALID;
+  if (count == 0) return MSCNN_OK;
+  relu_f32_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(x, count);
+  return launch_check("relu_f32");
+}
+
+extern "C" int mscnn_concat_planes(const void* x, void* y, size_t pixels, int C, int Ctot, int offset,
+                                   void* stream) {
+  if (!x || !y || C % 8 || Ctot % 8 || offset % 8 || offset + C > Ctot) return MSCNN_ERR_INVALID;
+  if (pixels == 0) return MSCNN_OK;
+  concat_planes_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)y, pixels, C, Ctot, offset);
+  return launch_check("concat_planes");
 }

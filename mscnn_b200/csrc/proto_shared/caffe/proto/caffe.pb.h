@@ -1,8 +1,10 @@
-// Hand-written stand-in for the protoc-generated caffe.pb.h (no protoc / libprotobuf in the
+// Hand-written equivalent of the protoc-generated caffe.pb.h (no protoc / libprotobuf in the
 // image).  It declares, with the field names, types and DEFAULTS of
-// /root/reference/src/caffe/proto/caffe.proto, exactly the messages and accessors that the
-// reference's hot-path sources use (census in SURVEY.md section 8(c)).  It is test
-// infrastructure for oracle/_ref only and is never linked into the product.
+// /root/reference/src/caffe/proto/caffe.proto, the messages and accessors that the MS-CNN
+// deploy nets and the hot-path layers use (census in SURVEY.md section 8(c)), with the same
+// generated-code API surface (name(), has_name(), set_name(), name_size(), add_name(),
+// mutable_name(), clear_name()).  Used by the Caffe-API mirror (csrc/caffe_api) and, so that the
+// verbatim reference build sees identical parameters, by oracle/_ref.
 #pragma once
 #include <stdint.h>
 
@@ -63,6 +65,7 @@ class RepeatedField : public std::vector<T> {
   const std::string& name(int i) const { return name##_[i]; }             \
   const RepeatedField<std::string>& name() const { return name##_; }      \
   void add_##name(const std::string& v) { name##_.push_back(v); }         \
+  void set_##name(int i, const std::string& v) { name##_[i] = v; }        \
   void clear_##name() { name##_.clear(); }
 
 #define PB_MSG(Type, name)                                              \
@@ -275,6 +278,26 @@ class LayerParameter {  // caffe.proto:310-414 (fields used by the deploy nets' 
   PB_MSG(ROIPoolingParameter, roi_pooling_param)
   PB_MSG(BoxOutputParameter, box_output_param)
   PB_MSG(BBoxRegParameter, bbox_reg_param)
+};
+
+class NetState {  // caffe.proto:257-261
+  PB_OPT(Phase, phase, TEST)
+  PB_OPT(int32_t, level, 0)
+  PB_REP_STR(stage)
+};
+
+class NetParameter {  // caffe.proto:64-100
+ public:
+  void Clear() { *this = NetParameter(); }
+  void CopyFrom(const NetParameter& o) { *this = o; }
+  PB_STR(name, "")
+  PB_REP_STR(input)
+  PB_REP_MSG(BlobShape, input_shape)
+  PB_REP(int32_t, input_dim)
+  PB_OPT(bool, force_backward, false)
+  PB_MSG(NetState, state)
+  PB_OPT(bool, debug_info, false)
+  PB_REP_MSG(LayerParameter, layer)
 };
 
 }  // namespace caffe

@@ -17,4 +17,4 @@ int tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t row
 
 }  // namespace mscnn
 
-extern "C" int mscnn_sm_count(void);
+#include "mscnn_b200.h"  // mscnn_sm_count

@@ -39,8 +39,8 @@ OWN_SOURCES = [SHIM / "cblas_shim.cpp", ROOT / "oracle" / "ref_harness.cpp"]
 
 # -O2 without -march=native / -ffast-math: the reference Makefile's release flags
 # (Makefile:318-322 "-DNDEBUG -O2"); keeps x86-64 baseline FP semantics (no FMA contraction).
-CXXFLAGS = ["-std=c++14", "-O2", "-DNDEBUG", "-DCPU_ONLY", "-fPIC", "-fopenmp", "-w",
-            "-I", str(SHIM), "-I", str(REF / "include"), "-I", str(ROOT / "mscnn_b200" / "csrc" / "caffe")]
+CXXFLAGS = ["-std=c++14", "-O2", "-DNDEBUG", "-DCPU_ONLY", "-fPIC", "-fopenmp", "-w", "-fvisibility=hidden", "-fno-gnu-unique",
+            "-I", str(SHIM), "-I", str(ROOT / "mscnn_b200" / "csrc" / "proto_shared"), "-I", str(REF / "include")]
 
 
 def available() -> bool:
@@ -51,7 +51,7 @@ def build(force: bool = False) -> Path | None:
     if not REF.exists():
         return LIB if LIB.exists() else None
     srcs = [REF / s for s in REF_SOURCES] + OWN_SOURCES
-    deps = srcs + list(SHIM.rglob("*.h*")) + [ROOT / "mscnn_b200/csrc/caffe/prototxt.hpp", Path(__file__)]
+    deps = srcs + list(SHIM.rglob("*.h*")) + list((ROOT / "mscnn_b200/csrc/proto_shared").rglob("*.h*")) + [Path(__file__)]
     if LIB.exists() and not force and all(d.stat().st_mtime <= LIB.stat().st_mtime for d in deps):
         return LIB
     obj = OUT / "obj"
@@ -66,7 +66,7 @@ def build(force: bool = False) -> Path | None:
 
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(cc, srcs))
-    r = subprocess.run(["g++", "-shared", "-fopenmp", "-o", str(LIB), *map(str, objs), "-ldl"],
+    r = subprocess.run(["g++", "-shared", "-fopenmp", "-Wl,-Bsymbolic", "-o", str(LIB), *map(str, objs), "-ldl"],
                        capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr[-4000:])

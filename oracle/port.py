@@ -184,6 +184,8 @@ def detect_postprocess(proposals_score, cls_pred, bbox_pred, cls_id=2, bbox_mean
     (1-based).  MATLAB computes the decode in single precision and bbNms in double."""
     f = np.float32
     p = _f32(proposals_score).reshape(-1, 6)[:, 1:].copy()          # :77
+    if len(p) == 0:
+        return np.zeros((0, 5), dtype=np.float32)
     p[:, 2] = p[:, 2] - p[:, 0]
     p[:, 3] = p[:, 3] - p[:, 1]                                      # :78
     cls_pred = _f32(cls_pred).reshape(len(p), -1)

@@ -26,6 +26,7 @@
 #include "caffe/layers/relu_layer.hpp"
 #include "caffe/proto/caffe.pb.h"
 #include "cblas.h"
+#include "proto_text.hpp"
 #include "prototxt.hpp"
 
 namespace caffe {
@@ -56,124 +57,6 @@ using caffe::Layer;
 using caffe::LayerParameter;
 using prototxt::Node;
 
-void fill_filler(const Node* n, caffe::FillerParameter* f) {
-  if (!n) return;
-  if (n->has("type")) f->set_type(n->str("type"));
-  if (n->has("value")) f->set_value((float)n->num("value", 0));
-  if (n->has("min")) f->set_min((float)n->num("min", 0));
-  if (n->has("max")) f->set_max((float)n->num("max", 1));
-  if (n->has("mean")) f->set_mean((float)n->num("mean", 0));
-  if (n->has("std")) f->set_std((float)n->num("std", 1));
-  if (n->has("sparse")) f->set_sparse((int)n->num("sparse", -1));
-}
-
-void fill_layer_param(const Node& n, LayerParameter* lp) {
-  lp->set_name(n.str("name"));
-  lp->set_type(n.str("type"));
-  for (const std::string& s : n.strs("bottom")) lp->add_bottom(s);
-  for (const std::string& s : n.strs("top")) lp->add_top(s);
-  lp->set_phase(caffe::TEST);
-  for (const prototxt::Field* f : n.all("param")) {
-    caffe::ParamSpec* ps = lp->add_param();
-    if (f->is_message) {
-      if (f->message->has("lr_mult")) ps->set_lr_mult((float)f->message->num("lr_mult", 1));
-      if (f->message->has("decay_mult")) ps->set_decay_mult((float)f->message->num("decay_mult", 1));
-    }
-  }
-  if (const Node* c = n.child("convolution_param")) {
-    caffe::ConvolutionParameter* p = lp->mutable_convolution_param();
-    if (c->has("num_output")) p->set_num_output((uint32_t)c->num("num_output", 0));
-    if (c->has("bias_term")) p->set_bias_term(c->boolean("bias_term", true));
-    for (double v : c->nums("pad")) p->add_pad((uint32_t)v);
-    for (double v : c->nums("kernel_size")) p->add_kernel_size((uint32_t)v);
-    for (double v : c->nums("stride")) p->add_stride((uint32_t)v);
-    for (double v : c->nums("dilation")) p->add_dilation((uint32_t)v);
-    if (c->has("pad_h")) p->set_pad_h((uint32_t)c->num("pad_h", 0));
-    if (c->has("pad_w")) p->set_pad_w((uint32_t)c->num("pad_w", 0));
-    if (c->has("kernel_h")) p->set_kernel_h((uint32_t)c->num("kernel_h", 0));
-    if (c->has("kernel_w")) p->set_kernel_w((uint32_t)c->num("kernel_w", 0));
-    if (c->has("stride_h")) p->set_stride_h((uint32_t)c->num("stride_h", 0));
-    if (c->has("stride_w")) p->set_stride_w((uint32_t)c->num("stride_w", 0));
-    if (c->has("group")) p->set_group((uint32_t)c->num("group", 1));
-    if (c->has("axis")) p->set_axis((int)c->num("axis", 1));
-    if (c->child("weight_filler")) fill_filler(c->child("weight_filler"), p->mutable_weight_filler());
-    if (c->child("bias_filler")) fill_filler(c->child("bias_filler"), p->mutable_bias_filler());
-  }
-  if (const Node* c = n.child("pooling_param")) {
-    caffe::PoolingParameter* p = lp->mutable_pooling_param();
-    if (c->has("pool")) {
-      const std::string m = c->str("pool");
-      p->set_pool(m == "AVE" ? caffe::PoolingParameter_PoolMethod_AVE
-                  : m == "STOCHASTIC" ? caffe::PoolingParameter_PoolMethod_STOCHASTIC
-                                      : caffe::PoolingParameter_PoolMethod_MAX);
-    }
-    if (c->has("pad")) p->set_pad((uint32_t)c->num("pad", 0));
-    if (c->has("pad_h")) p->set_pad_h((uint32_t)c->num("pad_h", 0));
-    if (c->has("pad_w")) p->set_pad_w((uint32_t)c->num("pad_w", 0));
-    if (c->has("kernel_size")) p->set_kernel_size((uint32_t)c->num("kernel_size", 0));
-    if (c->has("kernel_h")) p->set_kernel_h((uint32_t)c->num("kernel_h", 0));
-    if (c->has("kernel_w")) p->set_kernel_w((uint32_t)c->num("kernel_w", 0));
-    if (c->has("stride")) p->set_stride((uint32_t)c->num("stride", 1));
-    if (c->has("stride_h")) p->set_stride_h((uint32_t)c->num("stride_h", 0));
-    if (c->has("stride_w")) p->set_stride_w((uint32_t)c->num("stride_w", 0));
-    if (c->has("global_pooling")) p->set_global_pooling(c->boolean("global_pooling", false));
-  }
-  if (const Node* c = n.child("inner_product_param")) {
-    caffe::InnerProductParameter* p = lp->mutable_inner_product_param();
-    if (c->has("num_output")) p->set_num_output((uint32_t)c->num("num_output", 0));
-    if (c->has("bias_term")) p->set_bias_term(c->boolean("bias_term", true));
-    if (c->has("axis")) p->set_axis((int)c->num("axis", 1));
-    if (c->has("transpose")) p->set_transpose(c->boolean("transpose", false));
-    if (c->child("weight_filler")) fill_filler(c->child("weight_filler"), p->mutable_weight_filler());
-    if (c->child("bias_filler")) fill_filler(c->child("bias_filler"), p->mutable_bias_filler());
-  }
-  if (const Node* c = n.child("input_param")) {
-    for (const prototxt::Field* f : c->all("shape")) {
-      caffe::BlobShape* s = lp->mutable_input_param()->add_shape();
-      if (f->is_message)
-        for (double d : f->message->nums("dim")) s->add_dim((int64_t)d);
-    }
-  }
-  if (const Node* c = n.child("dropout_param")) {
-    if (c->has("dropout_ratio"))
-      lp->mutable_dropout_param()->set_dropout_ratio((float)c->num("dropout_ratio", 0.5));
-  }
-  if (const Node* c = n.child("concat_param")) {
-    if (c->has("axis")) lp->mutable_concat_param()->set_axis((int)c->num("axis", 1));
-    if (c->has("concat_dim")) lp->mutable_concat_param()->set_concat_dim((uint32_t)c->num("concat_dim", 1));
-  }
-  if (const Node* c = n.child("relu_param")) {
-    if (c->has("negative_slope"))
-      lp->mutable_relu_param()->set_negative_slope((float)c->num("negative_slope", 0));
-  }
-  if (const Node* c = n.child("roi_pooling_param")) {
-    caffe::ROIPoolingParameter* p = lp->mutable_roi_pooling_param();
-    if (c->has("pooled_h")) p->set_pooled_h((uint32_t)c->num("pooled_h", 0));
-    if (c->has("pooled_w")) p->set_pooled_w((uint32_t)c->num("pooled_w", 0));
-    if (c->has("spatial_scale")) p->set_spatial_scale((float)c->num("spatial_scale", 1));
-    if (c->has("pad_ratio")) p->set_pad_ratio((float)c->num("pad_ratio", 0));
-  }
-  if (const Node* c = n.child("box_output_param")) {
-    caffe::BoxOutputParameter* p = lp->mutable_box_output_param();
-    if (c->has("fg_thr")) p->set_fg_thr((float)c->num("fg_thr", 0));
-    if (c->has("iou_thr")) p->set_iou_thr((float)c->num("iou_thr", 0.5));
-    if (c->has("nms_type")) p->set_nms_type(c->str("nms_type"));
-    for (double v : c->nums("field_h")) p->add_field_h((uint32_t)v);
-    for (double v : c->nums("field_w")) p->add_field_w((uint32_t)v);
-    for (double v : c->nums("downsample_rate")) p->add_downsample_rate((uint32_t)v);
-    if (c->has("field_whr")) p->set_field_whr((float)c->num("field_whr", 2));
-    if (c->has("field_xyr")) p->set_field_xyr((float)c->num("field_xyr", 2));
-    if (c->has("max_nms_num")) p->set_max_nms_num((uint32_t)c->num("max_nms_num", 0));
-    if (c->has("max_post_nms_num")) p->set_max_post_nms_num((uint32_t)c->num("max_post_nms_num", 0));
-    if (c->has("min_size")) p->set_min_size((float)c->num("min_size", 15));
-  }
-  if (const Node* c = n.child("bbox_reg_param")) {
-    caffe::BBoxRegParameter* p = lp->mutable_bbox_reg_param();
-    for (double v : c->nums("bbox_mean")) p->add_bbox_mean((float)v);
-    for (double v : c->nums("bbox_std")) p->add_bbox_std((float)v);
-  }
-}
-
 struct RefLayer {
   LayerParameter param;
   boost::shared_ptr<Layer<float> > layer;
@@ -196,32 +79,13 @@ struct RefNet {
   }
 
   void build(const Node& root, int n_override) {
+    caffe::NetParameter np;
+    caffe::proto_text::fill(root, &np);
+    caffe::proto_text::UpgradeNetInput(&np);  // upgrade_proto.cpp:966-1000 semantics
     std::vector<LayerParameter> params;
-    // legacy `input:` + `input_dim:` x4 -> Input layer (upgrade_proto.cpp:966-1000)
-    const std::vector<std::string> inputs = root.strs("input");
-    if (!inputs.empty()) {
-      const std::vector<double> dims = root.nums("input_dim");
-      LayerParameter lp;
-      lp.set_name("input");
-      lp.set_type("Input");
-      lp.set_phase(caffe::TEST);
-      for (size_t i = 0; i < inputs.size(); ++i) {
-        lp.add_top(inputs[i]);
-        caffe::BlobShape* s = lp.mutable_input_param()->add_shape();
-        for (int d = 0; d < 4 && i * 4 + d < dims.size(); ++d) s->add_dim((int64_t)dims[i * 4 + d]);
-      }
-      for (const prototxt::Field* f : root.all("input_shape")) {
-        caffe::BlobShape* s = lp.mutable_input_param()->add_shape();
-        if (f->is_message)
-          for (double d : f->message->nums("dim")) s->add_dim((int64_t)d);
-      }
-      params.push_back(lp);
-    }
-    for (const prototxt::Field* f : root.all("layer")) {
-      if (!f->is_message) continue;
-      LayerParameter lp;
-      fill_layer_param(*f->message, &lp);
-      params.push_back(lp);
+    for (int i = 0; i < np.layer_size(); ++i) {
+      params.push_back(np.layer(i));
+      params.back().set_phase(caffe::TEST);
     }
     if (n_override > 0) {
       for (LayerParameter& lp : params) {
@@ -256,6 +120,7 @@ struct RefNet {
 
 }  // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 void* mscnn_ref_net_create(const char* prototxt_or_path, int is_path, int n_override) {
@@ -349,3 +214,4 @@ double mscnn_ref_net_forward(void* h, int from, int to, double* per_layer_ms) {
   return total;
 }
 }
+#pragma GCC visibility pop

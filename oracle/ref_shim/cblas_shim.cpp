@@ -141,6 +141,7 @@ void gemv_builtin(bool ta, int M, int N, T alpha, const T* A, int lda, const T* 
 
 }  // namespace
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 const char* mscnn_ref_blas_backend(void) { return backend().name.c_str(); }
@@ -215,3 +216,4 @@ void cblas_dcopy(const int N, const double* X, const int ix, double* Y, const in
   for (int i = 0; i < N; ++i) Y[(size_t)i * iy] = X[(size_t)i * ix];
 }
 }
+#pragma GCC visibility pop

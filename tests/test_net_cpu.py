@@ -1,0 +1,134 @@
+"""Host-side logic of the drop-in boundary, runnable without a GPU: the text-format reader, the
+Caffe-API mirror's Net construction (split insertion, blob names and shapes, output order,
+parameter shapes), the generated model zoo, and the exported C ABI."""
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+REF_EX = Path("/root/reference/examples")
+
+
+def test_capi_exports_every_declared_symbol():
+    from mscnn_b200 import capi
+    L = capi.lib()
+    hdr = (ROOT / "include" / "mscnn_b200.h").read_text()
+    names = sorted(set(re.findall(r"\b(mscnn_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 20
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, f"declared in include/mscnn_b200.h but not exported: {missing}"
+    assert b"sm_100a" in L.mscnn_version()
+
+
+def test_library_carries_sm100a_tensor_core_code():
+    out = subprocess.run(["cuobjdump", "-sass", str(ROOT / "mscnn_b200" / "libmscnn_b200.so")],
+                         capture_output=True, text=True).stdout
+    if not out:
+        pytest.skip("cuobjdump unavailable")
+    assert "UTCHMMA" in out and "UTMALDG" in out and "UTMASTG" in out and "LDTM" in out
+
+
+def test_net_kitti_8s_structure():
+    from mscnn_b200 import models
+    from mscnn_b200.net import Net
+    net = Net(models.kitti(768, 2560, 8))
+    assert net.inputs == ["data"]
+    assert net.outputs == ["bbox_pred", "cls_pred", "proposals_score"]       # name order, net.cpp:268-274
+    # InsertSplits names after the LAST writer (the in-place ReLU), insert_splits.cpp:37-40,110-124
+    for k in range(4):
+        assert f"conv4_3_relu4_3_0_split_{k}" in net.blob_names
+    assert "proposals_proposals_0_split_0" in net.blob_names
+    assert net.blob_shape("data") == (1, 3, 768, 2560)
+    assert net.blob_shape("conv1_2") == (1, 64, 768, 2560)
+    assert net.blob_shape("conv4_3") == (1, 512, 96, 320)
+    assert net.blob_shape("pool6") == (1, 512, 12, 40)
+    assert net.blob_shape("LFCN_4_7x7") == (1, 9, 12, 40)
+    assert net.blob_shape("proposals") == (1, 5, 1, 1)                       # dummy reshape
+    assert net.blob_shape("roi_pool") == (1, 1024, 7, 7)
+    assert net.blob_shape("roi_c1") == (1, 512, 5, 5)
+    assert net.blob_shape("fc6") == (1, 4096) and net.blob_shape("bbox_pred") == (1, 20)
+    assert net.param_shapes("conv1_1") == [(64, 3, 3, 3), (64,)]
+    assert net.param_shapes("LFCN_1_7x7") == [(9, 512, 7, 7), (9,)]
+    assert net.param_shapes("fc6") == [(4096, 12800), (4096,)]
+    assert net.layer_types.count("Split") == 7   # conv4_3, loss1_conv1, conv5_3, conv6_1, pool6, proposals, fc6
+
+
+def test_net_reshape_input_propagates():
+    from mscnn_b200 import models
+    from mscnn_b200.net import Net
+    net = Net(models.kitti(576, 1920, 7, up2x=True))
+    net.reshape_input("data", 2, 3, 192, 640)
+    assert net.blob_shape("conv4_3") == (2, 512, 24, 80)
+    assert net.blob_shape("conv4_3_2x") == (2, 512, 48, 160)
+    assert net.blob_shape("LFCN_4_5x5") == (2, 9, 3, 10)
+
+
+def test_widerface_structure():
+    from mscnn_b200 import models
+    from mscnn_b200.net import Net
+    net = Net(models.widerface(768, 1024, batch=2))
+    assert net.blob_shape("LFCN_1_12x12") == (2, 6, 96, 128)
+    assert net.blob_shape("pool6") == (2, 512, 12, 16)
+    assert net.blob_shape("roi_c1") == (1, 512, 5, 5) and net.blob_shape("fc6") == (1, 2048)
+    assert net.param_shapes("conv4_3_2x") == [(512, 1, 4, 4)]
+
+
+def test_prototxt_syntax_quirks():
+    """Comments (also trailing), `field: { }` and `field { }`, several pairs per line, negative and
+    float values, enums and strings -- all present in the shipped deploy files."""
+    from mscnn_b200.net import Net
+    text = '''name: "q"  # a comment
+input: "data" input_dim: 1 input_dim: 64 input_dim: 8 input_dim: 8
+layer { bottom: "data" top: "c" name: "c" type: "Convolution"
+  param { lr_mult: 1 decay_mult: 1 } param { lr_mult: 2 decay_mult: 0 }
+  convolution_param { num_output: 6 kernel_size: 3
+    #pad: 1
+    weight_filler: { type: "gaussian" std: 0.01 } bias_filler { type: "constant" value: -0.5 } } }
+layer { bottom: "c" top: "p" name: "p" type: "Pooling" pooling_param { pool: AVE kernel_size: 2 stride: 2 } propagate_down: 0 }
+'''
+    net = Net(text)
+    assert net.blob_shape("c") == (1, 6, 6, 6) and net.blob_shape("p") == (1, 6, 3, 3)
+
+
+def test_unknown_field_is_rejected():
+    from mscnn_b200 import capi
+    from mscnn_b200.net import Net
+    with pytest.raises(capi.MscnnError):
+        Net('input: "d" input_dim: 1 input_dim: 1 input_dim: 4 input_dim: 4\n'
+            'layer { bottom: "d" top: "p" name: "p" type: "Pooling" pooling_param { kernel_size: 2 bogus_field: 3 } }\n')
+
+
+@pytest.mark.skipif(not REF_EX.exists(), reason="reference tree not mounted")
+@pytest.mark.parametrize("ref_path,gen", [
+    ("kitti_car/mscnn-8s-768-trainval", ("kitti", (768, 2560, 8, False))),
+    ("kitti_car/mscnn-7s-576", ("kitti", (576, 1920, 7, False))),
+    ("kitti_car/mscnn-7s-576-2x", ("kitti", (576, 1920, 7, True))),
+    ("widerface/mscnn-12s-2x", ("widerface", (512, 512))),
+])
+def test_shipped_deploy_files_load_unchanged_and_match_generated(ref_path, gen):
+    from mscnn_b200 import models
+    from mscnn_b200.net import Net
+    shipped = Net(str(REF_EX / ref_path / "mscnn_deploy.prototxt"))
+    generated = Net(getattr(models, gen[0])(*gen[1]))
+    assert shipped.layer_names == generated.layer_names
+    assert shipped.layer_types == generated.layer_types
+    assert shipped.blob_names == generated.blob_names
+    assert shipped.layers() == generated.layers()
+    assert [shipped.blob_shape(b) for b in shipped.blob_names] == [generated.blob_shape(b) for b in generated.blob_names]
+    assert shipped.layer_param_strings() == generated.layer_param_strings()
+
+
+def test_synth_is_deterministic_and_name_keyed():
+    from mscnn_b200 import synth
+    layers = [("conv1_1", "Convolution", [(64, 3, 3, 3), (64,)]), ("LFCN_1_5x5", "Convolution", [(9, 512, 5, 5), (9,)]),
+              ("conv4_3_2x", "Deconvolution", [(512, 1, 4, 4)])]
+    a, b = synth.make_weights(layers), synth.make_weights(list(reversed(layers)))
+    for k in a:
+        assert all(np.array_equal(x, y) for x, y in zip(a[k], b[k]))
+    assert a["LFCN_1_5x5"][1][0] == synth.BG_BIAS and a["conv4_3_2x"][0][5, 0, 1, 1] == np.float32(0.5625)
+    img = synth.make_images(2, 8, 8)
+    assert img.shape == (2, 3, 8, 8) and img[0, 0].max() <= 255 - 104 and img[0, 2].min() >= -123
+    assert np.array_equal(synth.make_images(1, 8, 8, first_index=1)[0], img[1])
