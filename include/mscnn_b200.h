@@ -47,6 +47,7 @@ extern "C" {
 
 #define MSCNN_OUT_NHWC_BF16 0 /* planes, via TMA store */
 #define MSCNN_OUT_NCHW_F32 1  /* Caffe blob layout, fp32 */
+#define MSCNN_OUT_NHWC_F32 2  /* pixel-major fp32 rows [N*Ho*Wo][Cout_pad] (head-tap partial sums) */
 
 #define MSCNN_POOL_MAX 0
 #define MSCNN_POOL_AVE 1
@@ -71,6 +72,7 @@ MSCNN_API int mscnn_sm_count(void);
  *   bias: fp32 [Cout_pad]
  *   out : MSCNN_OUT_NHWC_BF16 -> y planes [N][Ho][Wo][Cout_pad] (Cout_pad % 64 == 0)
  *         MSCNN_OUT_NCHW_F32  -> y_f32 [N][Cout][Ho][Wo]
+ *         MSCNN_OUT_NHWC_F32  -> y_f32 [N][Ho][Wo][Cout_pad]
  *   Ho = H + 2 pad_h - KH + 1, Wo likewise.  InnerProduct = KH = KW = H = W = 1.
  */
 typedef struct mscnn_conv_desc {
@@ -98,6 +100,27 @@ MSCNN_API int mscnn_pack_conv_weights(const float* w_f32, void* w_hi, void* w_lo
                             int KW, int Cout_pad, int Cin_pad, void* stream);
 MSCNN_API int mscnn_pack_fc_weights(const float* w_f32, void* w_hi, void* w_lo, int Nout, int C, int H, int W,
                           int Nout_pad, int Cpad, void* stream);
+
+/* First trunk convolution (3 input channels, 3x3, pad 1, stride 1) in exact fp32 on the CUDA cores,
+ * fused bias + ReLU, planes out.  x: fp32 NCHW [N][3][H][W] (the net input blob), w: fp32
+ * [Cout][3][3][3] (layer blob 0 as is), y planes [N][H][W][Cout_pad].  Replaces
+ * ConvolutionLayer::Forward_gpu for conv1_1 (conv_layer.cu:8-23); K = 27 is too short for a
+ * tensor-core k-block, the layer is bound by its output traffic. */
+MSCNN_API int mscnn_conv3x3_c3_forward(const float* x, const float* w, const float* bias, void* y_hi, void* y_lo,
+                             int N, int H, int W, int Cout, int Cout_pad, int relu, void* stream);
+
+/* Narrow-output k x k heads (LFCN_*: Cout = 9, k = 5 / 7) as ONE 1x1 GEMM plus a gather.
+ * A k x k conv with tiny Cout wastes the tensor core (N = 16..32) and re-reads the activation tile
+ * once per tap; instead taps move into the GEMM's N dimension:
+ *   P[pixel][tap*Cout + co] = sum_c x[pixel][c] * w[co][c][tap]        (mscnn_conv_forward, 1x1,
+ *                                                                        MSCNN_OUT_NHWC_F32, N = k*k*Cout)
+ *   y[n][co][h][w] = bias[co] + sum_tap P[(n, h+dy-pad, w+dx-pad)][tap*Cout + co]   (mscnn_head_gather)
+ * Same FLOPs as the convolution, the activation is read once, summation order differs from
+ * im2col+sgemm only in fp32 rounding.  Replaces ConvolutionLayer::Forward_gpu for those layers. */
+MSCNN_API int mscnn_pack_head_weights(const float* w_f32 /*[Cout][Cin][k][k]*/, void* w_hi, void* w_lo, int Cout,
+                            int Cin, int k, int N_pad, int Cin_pad, void* stream);
+MSCNN_API int mscnn_head_gather(const float* P, int ld, const float* bias, float* y /*[N][Cout][H][W]*/, int N, int H,
+                      int W, int Cout, int k, int pad, void* stream);
 
 /* Layout converters between Caffe blobs (NCHW fp32, blob.hpp:153-164) and planes. */
 MSCNN_API int mscnn_nchw_f32_to_planes(const float* x, void* hi, void* lo, int N, int C, int H, int W,

@@ -238,14 +238,17 @@ __global__ void nms_mask_kernel(const float4* __restrict__ boxes, const int* __r
   mask[((size_t)n * Kpad + i) * words + cb] = bits;
 }
 
-// Greedy scan (nmsMax with greedy=true, box_output_layer.cpp:46-56).  One CTA per image.
-constexpr int kScanThreads = 128;
+// Greedy scan (nmsMax with greedy=true, box_output_layer.cpp:46-56).  One CTA per image walks the
+// boxes in blocks of 64: the block's mask rows are staged in shared memory with coalesced loads,
+// one thread resolves the 64 intra-block decisions on the diagonal word, then every thread ORs
+// the kept rows into the suppression words of the later blocks.
+constexpr int kScanThreads = 256;
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ counts, int Kpad,
                 int words, int max_post, int* __restrict__ keep_idx, int* __restrict__ keep_count) {
+  extern __shared__ unsigned long long tile[];  // [64][words]
   __shared__ unsigned long long remv[128];
   __shared__ unsigned long long kept[128];
-  __shared__ unsigned long long diag[64];
   __shared__ unsigned long long s_keptbits;
   const int n = blockIdx.x, tid = threadIdx.x;
   const int M = counts[n];
@@ -255,14 +258,18 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
   __syncthreads();
   for (int b = 0; b < nb; ++b) {
     const int rows = min(64, M - b * 64);
-    if (tid < rows) diag[tid] = mk[(size_t)(b * 64 + tid) * words + b];
+    const int wcount = nb - b;
+    for (int idx = tid; idx < rows * wcount; idx += kScanThreads) {
+      const int r = idx / wcount, w = b + idx - r * wcount;
+      tile[r * words + w] = mk[(size_t)(b * 64 + r) * words + w];
+    }
     __syncthreads();
     if (tid == 0) {
       unsigned long long cur = remv[b], kb = 0ull;
       for (int i = 0; i < rows; ++i) {
         if (!((cur >> i) & 1ull)) {
           kb |= (1ull << i);
-          cur |= diag[i];
+          cur |= tile[i * words + b];
         }
       }
       s_keptbits = kb;
@@ -276,7 +283,7 @@ nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restri
       while (bits) {
         const int i = __ffsll((long long)bits) - 1;
         bits &= bits - 1;
-        acc |= mk[(size_t)(b * 64 + i) * words + w];
+        acc |= tile[i * words + w];
       }
       remv[w] = acc;
     }
@@ -586,8 +593,11 @@ extern "C" int mscnn_box_output_forward(const mscnn_box_output_cfg* cfg, int N, 
   const int words = Kpad / 64;
   nms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words, cfg->iou_thr,
                                                            cfg->nms_type, mask);
-  nms_scan_kernel<<<N, kScanThreads, 0, stream>>>(mask, counts, Kpad, words, cfg->max_post_nms_num,
-                                                  keep_idx, keep_count);
+  const size_t scan_smem = (size_t)64 * words * 8;
+  e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+  if (e != cudaSuccess) return MSCNN_ERR_CUDA;
+  nms_scan_kernel<<<N, kScanThreads, scan_smem, stream>>>(mask, counts, Kpad, words, cfg->max_post_nms_num,
+                                                          keep_idx, keep_count);
   box_finalize_kernel<<<1, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, N, Kpad, proposals,
                                              proposals_score, num_out);
   e = cudaGetLastError();
@@ -672,7 +682,10 @@ extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, cons
   const int words = Kpad / 64;
   bbnms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words,
                                                              (double)cfg->nms_overlap, mask);
-  nms_scan_kernel<<<N, kScanThreads, 0, stream>>>(mask, counts, Kpad, words, 0, keep_idx, keep_count);
+  const size_t scan_smem = (size_t)64 * words * 8;
+  e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+  if (e != cudaSuccess) return MSCNN_ERR_CUDA;
+  nms_scan_kernel<<<N, kScanThreads, scan_smem, stream>>>(mask, counts, Kpad, words, 0, keep_idx, keep_count);
   detect_write_kernel<<<N, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, Kpad,
                                             cfg->max_rois_per_image, dets, det_counts);
   e = cudaGetLastError();

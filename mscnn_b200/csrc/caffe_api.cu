@@ -15,11 +15,22 @@ Caffe& Caffe::Get() {
   return *instance;
 }
 
-Caffe::Caffe() : mode_(Caffe::GPU), precision_(Caffe::FP32_SPLIT), stream_(0) {
+Caffe::Caffe() : mode_(Caffe::GPU), precision_(Caffe::FP32_SPLIT), stream_(0), scratch_(nullptr), scratch_bytes_(0) {
   if (const char* e = std::getenv("MSCNN_PRECISION")) {
     const std::string v(e);
     if (v == "bf16" || v == "BF16") precision_ = BF16;
   }
+}
+
+void* Caffe::scratch(size_t bytes) {
+  Caffe& c = Get();
+  if (bytes > c.scratch_bytes_) {
+    // the old buffer may still be in use by queued kernels: free is stream-ordered by the driver
+    if (c.scratch_) CUDA_CHECK(cudaFree(c.scratch_));
+    CUDA_CHECK(cudaMalloc(&c.scratch_, bytes));
+    c.scratch_bytes_ = bytes;
+  }
+  return c.scratch_;
 }
 
 void Caffe::SetDevice(const int device_id) { CUDA_CHECK(cudaSetDevice(device_id)); }

@@ -76,6 +76,9 @@ class Caffe {
   // the stream every layer launches on (the reference uses the legacy default stream)
   inline static cudaStream_t stream() { return Get().stream_; }
   inline static void set_stream(cudaStream_t s) { Get().stream_ = s; }
+  // Transient device scratch (grow-only, per thread context); valid until the next scratch() call
+  // on the same context.  Work using it is stream-ordered, so layers may reuse it back to back.
+  static void* scratch(size_t bytes);
   inline static int solver_count() { return 1; }
   inline static bool root_solver() { return true; }
 
@@ -84,6 +87,8 @@ class Caffe {
   Brew mode_;
   Precision precision_;
   cudaStream_t stream_;
+  void* scratch_;
+  size_t scratch_bytes_;
   DISABLE_COPY_AND_ASSIGN(Caffe);
 };
 

@@ -62,6 +62,10 @@ class ConvolutionLayer : public Layer<Dtype> {
   bool bias_term_, fuse_relu_;
   PackedParam packed_;
   PlaneStore patches_;  // conv1_1: 27-tap patch planes
+  float* head_bias_ = nullptr;        // narrow k x k heads: bias applied by the tap gather
+  unsigned long head_bias_version_ = ~0ul;
+ public:
+  virtual ~ConvolutionLayer();
 };
 
 /// DeconvolutionLayer: deconv_layer.cpp:8-40, restricted to the depthwise 4/2/1 bilinear-upsampling

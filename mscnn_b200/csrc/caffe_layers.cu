@@ -146,16 +146,73 @@ static void ensure_packed_conv(PackedParam* pk, Blob<float>* w, Blob<float>* b, 
 }
 
 template <typename Dtype>
+ConvolutionLayer<Dtype>::~ConvolutionLayer() {
+  if (head_bias_) cudaFree(head_bias_);
+}
+
+template <typename Dtype>
 void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
   const bool split = Caffe::split();
   const int N = bottom[0]->num(), H = bottom[0]->height(), W = bottom[0]->width();
   Blob<Dtype>* bias = bias_term_ ? this->blobs_[1].get() : nullptr;
   mscnn_conv_desc d;
   memset(&d, 0, sizeof(d));
+  // Narrow k x k proposal heads (LFCN_*: 9 or 6 outputs, 5x5 / 7x7, "same" padding): taps move
+  // into the GEMM's N dimension and a gather sums them (see mscnn_head_gather in the C ABI).
+  const bool head_path = (num_output_ == 9 || num_output_ == 6) && kernel_h_ == kernel_w_ && kernel_h_ > 1 &&
+                         pad_h_ == pad_w_ && 2 * pad_h_ + 1 == kernel_h_ && !fuse_relu_ && channels_ % 64 == 0 &&
+                         !std::getenv("MSCNN_NO_HEAD_TAPS");
+  if (head_path) {
+    const int k = kernel_h_, taps = k * k;
+    const int n_pad = (taps * num_output_ + 255) / 256 * 256;
+    Blob<Dtype>* wb = this->blobs_[0].get();
+    if (packed_.w_version != wb->version() || packed_.split != split || packed_.cout_pad != n_pad) {
+      packed_.w.reserve((size_t)n_pad * channels_ * 2, split);
+      MSCNN_CHECK(mscnn_pack_head_weights(wb->gpu_data(), packed_.w.hi, split ? packed_.w.lo : nullptr, num_output_,
+                                          channels_, k, n_pad, channels_, Caffe::stream()));
+      if (packed_.bias) CUDA_CHECK(cudaFree(packed_.bias));
+      CUDA_CHECK(cudaMalloc(&packed_.bias, sizeof(float) * n_pad));
+      CUDA_CHECK(cudaMemsetAsync(packed_.bias, 0, sizeof(float) * n_pad, Caffe::stream()));  // bias is added later
+      packed_.w_version = wb->version();
+      packed_.split = split;
+      packed_.cout_pad = n_pad;
+    }
+    const unsigned long bver = bias ? bias->version() : 0;
+    if (!head_bias_ || head_bias_version_ != bver) {
+      if (!head_bias_) CUDA_CHECK(cudaMalloc(&head_bias_, sizeof(float) * num_output_));
+      CUDA_CHECK(cudaMemsetAsync(head_bias_, 0, sizeof(float) * num_output_, Caffe::stream()));
+      if (bias)
+        CUDA_CHECK(cudaMemcpyAsync(head_bias_, bias->gpu_data(), sizeof(float) * num_output_,
+                                   cudaMemcpyDeviceToDevice, Caffe::stream()));
+      head_bias_version_ = bver;
+    }
+    typename Blob<Dtype>::Planes x = bottom[0]->planes(split);
+    float* P = static_cast<float*>(Caffe::scratch((size_t)N * H * W * n_pad * sizeof(float)));
+    d.x_hi = x.hi; d.x_lo = x.lo;
+    d.N = N; d.H = H; d.W = W; d.C = x.cpad;
+    d.w_hi = packed_.w.hi; d.w_lo = split ? packed_.w.lo : nullptr;
+    d.bias = packed_.bias;
+    d.Cout = n_pad; d.Cout_pad = n_pad;
+    d.KH = d.KW = 1;
+    d.out_mode = MSCNN_OUT_NHWC_F32;
+    d.y_f32 = P;
+    MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
+    MSCNN_CHECK(mscnn_head_gather(P, n_pad, head_bias_, top[0]->mutable_gpu_data(), N, H, W, num_output_, k, pad_h_,
+                                  Caffe::stream()));
+    return;
+  }
   // conv1_1-style layer (3 input channels, 3x3, pad 1): K = 27 is far below one 64-channel
-  // k-block, so the 27 taps are gathered into 64-channel patch planes and the layer runs as a
-  // 1x1 GEMM.  Weight order c*9 + dy*3 + dx is Caffe's own [Cout][Cin][kh][kw] flattening.
-  const bool patch_path = (channels_ == 3 && kernel_h_ == 3 && kernel_w_ == 3 && pad_h_ == 1 && pad_w_ == 1);
+  // tensor-core k-block; it runs as a direct exact-fp32 kernel straight from the NCHW input blob.
+  const bool first_path = (channels_ == 3 && kernel_h_ == 3 && kernel_w_ == 3 && pad_h_ == 1 && pad_w_ == 1);
+  if (first_path && !std::getenv("MSCNN_CONV1_GEMM")) {
+    typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
+    MSCNN_CHECK(mscnn_conv3x3_c3_forward(bottom[0]->gpu_data(), this->blobs_[0]->gpu_data(),
+                                         bias ? bias->gpu_data() : nullptr, y.hi, y.lo, N, H, W, num_output_,
+                                         y.cpad, fuse_relu_ ? 1 : 0, Caffe::stream()));
+    return;
+  }
+  // (MSCNN_CONV1_GEMM=1: the same layer as a 1x1 GEMM over 27-tap patch planes, kept for comparison)
+  const bool patch_path = first_path;
   if (patch_path) {
     ensure_packed_conv(&packed_, this->blobs_[0].get(), bias, split, num_output_, 27, 1, 1, 64);
     const size_t bytes = (size_t)N * H * W * 64 * 2;

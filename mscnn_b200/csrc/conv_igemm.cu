@@ -42,12 +42,13 @@ struct IgemmParams {
   int tiles_w, tiles_h, tiles_n, n_tiles;
   int box_w, box_h, box_n;
   int relu;
-  int out_mode;    // MSCNN_OUT_NHWC_BF16 or MSCNN_OUT_NCHW_F32
+  int out_mode;    // MSCNN_OUT_NHWC_BF16, MSCNN_OUT_NCHW_F32 or MSCNN_OUT_NHWC_F32
   int has_lo_out;
   int stages, epi_bufs;
   const float* bias;  // [Cout_pad]
   float* out_f32;     // NCHW fp32 (out_mode 1)
   int out_n, out_c, out_h, out_w;
+  int out_ld;         // row length of the pixel-major fp32 output (MSCNN_OUT_NHWC_F32)
 };
 
 constexpr int kBlockM = 128;
@@ -294,12 +295,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
         float* obase = p.out_f32 + (static_cast<size_t>(n) * p.out_c) * plane +
                        static_cast<size_t>(h) * p.out_w + w;
+        // pixel-major fp32 rows [pixel][ld]: each thread owns one 128-byte segment per chunk
+        float* rbase = p.out_f32 + ((static_cast<size_t>(n) * p.out_h + h) * p.out_w + w) * p.out_ld + n_base;
 #pragma unroll 1
         for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
           uint32_t v[32];
           ptx::tmem_ld_32x32(t_row + chunk * 32, v);
           ptx::tmem_ld_wait();
-          if (ok) {
+          if (p.out_mode == MSCNN_OUT_NHWC_F32) {
+            if (ok) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                o.x = __uint_as_float(v[j]) + bias_s[chunk * 32 + j];
+                o.y = __uint_as_float(v[j + 1]) + bias_s[chunk * 32 + j + 1];
+                o.z = __uint_as_float(v[j + 2]) + bias_s[chunk * 32 + j + 2];
+                o.w = __uint_as_float(v[j + 3]) + bias_s[chunk * 32 + j + 3];
+                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                *reinterpret_cast<float4*>(rbase + chunk * 32 + j) = o;
+              }
+            }
+          } else if (ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int ch = n_base + chunk * 32 + j;
@@ -392,7 +408,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   const int BN = pick_block_n(d->Cout_pad);
   if (d->Cout_pad % BN != 0 || d->Cout > d->Cout_pad) return MSCNN_ERR_INVALID;
   if (d->out_mode == MSCNN_OUT_NHWC_BF16 && (BN < 64 || !d->y_hi)) return MSCNN_ERR_INVALID;
-  if (d->out_mode == MSCNN_OUT_NCHW_F32 && !d->y_f32) return MSCNN_ERR_INVALID;
+  if ((d->out_mode == MSCNN_OUT_NCHW_F32 || d->out_mode == MSCNN_OUT_NHWC_F32) && !d->y_f32) return MSCNN_ERR_INVALID;
 
   IgemmParams p;
   memset(&p, 0, sizeof(p));
@@ -416,6 +432,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   p.out_c = d->Cout;
   p.out_h = Ho;
   p.out_w = Wo;
+  p.out_ld = d->Cout_pad;
 
   // shared memory plan
   const int b_bytes = BN * kBlockK * 2;

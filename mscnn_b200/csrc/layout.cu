@@ -157,6 +157,56 @@ __global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __r
   }
 }
 
+// out[(tap*Cout + co)][ci] = w[co][ci][tap]  (rows beyond taps*Cout and channels beyond Cin are zero)
+__global__ void pack_head_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                   __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int taps, int N_pad,
+                                   int Cin_pad) {
+  const size_t total = (size_t)N_pad * Cin_pad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const int ci = i % Cin_pad;
+    const int n = i / Cin_pad;
+    float v = 0.f;
+    if (n < taps * Cout && ci < Cin) {
+      const int tap = n / Cout, co = n - tap * Cout;
+      v = w[((size_t)co * Cin + ci) * taps + tap];
+    }
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+// One thread per output pixel; taps in (dy, dx) order like the reference's im2col column order.
+template <int COUT>
+__global__ void head_gather_kernel(const float* __restrict__ P, int ld, const float* __restrict__ bias,
+                                   float* __restrict__ y, int N, int H, int W, int k, int pad) {
+  const size_t total = (size_t)N * H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int w = idx % W;
+  const int h = (idx / W) % H;
+  const int n = idx / ((size_t)W * H);
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  for (int dy = 0; dy < k; ++dy) {
+    const int hh = h + dy - pad;
+    if (hh < 0 || hh >= H) continue;
+    for (int dx = 0; dx < k; ++dx) {
+      const int ww = w + dx - pad;
+      if (ww < 0 || ww >= W) continue;
+      const float* src = P + ((size_t)(n * H + hh) * W + ww) * ld + (dy * k + dx) * COUT;
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] = acc[c] + src[c];
+    }
+  }
+  const size_t plane = (size_t)H * W;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) y[((size_t)n * COUT + c) * plane + (size_t)h * W + w] = acc[c] + bias[c];
+}
+
 static int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -224,4 +274,29 @@ extern "C" int mscnn_pack_fc_weights(const float* w, void* hi, void* lo, int Nou
   pack_fc_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Nout, C, H * W, Nout_pad, Cpad);
   return check_launch("pack_fc_w");
+}
+
+extern "C" int mscnn_pack_head_weights(const float* w, void* hi, void* lo, int Cout, int Cin, int k, int N_pad,
+                                       int Cin_pad, void* stream) {
+  if (!w || !hi || Cout <= 0 || Cin <= 0 || k <= 0 || N_pad < k * k * Cout || Cin_pad < Cin || Cin_pad % 64)
+    return MSCNN_ERR_INVALID;
+  const size_t total = (size_t)N_pad * Cin_pad;
+  const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  pack_head_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout,
+                                                              Cin, k * k, N_pad, Cin_pad);
+  return check_launch("pack_head_w");
+}
+
+extern "C" int mscnn_head_gather(const float* P, int ld, const float* bias, float* y, int N, int H, int W,
+                                 int Cout, int k, int pad, void* stream) {
+  if (!P || !bias || !y || N <= 0 || H <= 0 || W <= 0 || k <= 0 || ld < k * k * Cout) return MSCNN_ERR_INVALID;
+  const size_t total = (size_t)N * H * W;
+  const unsigned blocks = (unsigned)((total + 127) / 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (Cout) {
+    case 6: head_gather_kernel<6><<<blocks, 128, 0, st>>>(P, ld, bias, y, N, H, W, k, pad); break;
+    case 9: head_gather_kernel<9><<<blocks, 128, 0, st>>>(P, ld, bias, y, N, H, W, k, pad); break;
+    default: return MSCNN_ERR_INVALID;  // the MS-CNN heads have cls_num + 4 = 6 or 9 channels
+  }
+  return check_launch("head_gather");
 }

@@ -238,3 +238,16 @@ def detect_postprocess(cfg: capi.DetectCfg, n: int, proposals_score, cls_pred, b
                                                    nbytes.value, capi.ptr(dets), capi.ptr(counts), _stream()),
                "detect_postprocess")
     return dets, counts
+
+
+def conv3x3_c3_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, relu: bool, split: bool) -> Planes:
+    """conv1_1 shape: x [N,3,H,W] fp32 NCHW, w [Cout,3,3,3] fp32 -> planes (direct fp32 kernel)."""
+    n, _, h, wd = x.shape
+    cout = w.shape[0]
+    cp = pad64(cout)
+    y_hi = torch.empty((n, h, wd, cp), dtype=torch.bfloat16, device=x.device)
+    y_lo = torch.empty_like(y_hi) if split else None
+    capi.check(capi.lib().mscnn_conv3x3_c3_forward(capi.ptr(x), capi.ptr(w), capi.ptr(b), capi.ptr(y_hi),
+                                                   capi.ptr(y_lo), n, h, wd, cout, cp, int(relu), _stream()),
+               "conv3x3_c3_forward")
+    return Planes(y_hi, y_lo, cout)

@@ -158,6 +158,27 @@ def test_conv1_1_im2col(cuda, split):
         _report("conv1_1", got, ref, 2.0 ** -8, 1e-5 * float(ref.pow(2).mean().sqrt()))
 
 
+@pytest.mark.parametrize("split", [True, False], ids=["split", "bf16"])
+def test_conv1_1_direct(cuda, split):
+    """conv1_1 as the direct exact-fp32 kernel (the path the Net uses)."""
+    from mscnn_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(4)
+    n, h, w = 2, 21, 150        # W crosses a 128-pixel tile boundary
+    x = (torch.randint(0, 256, (n, 3, h, w), generator=g).float()
+         - torch.tensor([104.0, 117.0, 123.0]).view(1, 3, 1, 1)).to(cuda).contiguous()
+    wt = (torch.randn((64, 3, 3, 3), generator=g) * (2.0 / 27) ** 0.5 / 64).to(cuda)
+    b = (torch.randn((64,), generator=g) * 0.1).to(cuda)
+    yp = ops.conv3x3_c3_forward(x, wt, b, relu=True, split=split)
+    got = ops.planes_to_nchw(yp)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, wt, b, 1, True)
+    rms = float(ref.pow(2).mean().sqrt())
+    if split:
+        _report("conv1_1_direct", got, ref, 2e-5, 2e-5 * rms)      # fp32 FMA + 2^-18 split of the output
+    else:
+        _report("conv1_1_direct", got, ref, 2.0 ** -8, 1e-5 * rms)
+
+
 def test_layout_roundtrip(cuda):
     from mscnn_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(5)
