@@ -239,6 +239,7 @@ MSCNN_API int mscnn_net_layer_param_string(void* net, int i, char* buf, int cap)
 MSCNN_API int mscnn_net_num_params(void* net, const char* layer);
 MSCNN_API int mscnn_net_param_shape(void* net, const char* layer, int idx, int* shape4); /* returns #axes */
 MSCNN_API int mscnn_net_set_param(void* net, const char* layer, int idx, const float* host, long count);
+MSCNN_API int mscnn_net_get_param(void* net, const char* layer, int idx, float* host, long count);
 MSCNN_API int mscnn_net_copy_trained(void* net, const char* caffemodel_path); /* Net::CopyTrainedLayersFrom */
 MSCNN_API int mscnn_net_num_blobs(void* net);
 MSCNN_API const char* mscnn_net_blob_name(void* net, int i);

@@ -126,6 +126,14 @@ int mscnn_net_set_param(void* h, const char* layer, int idx, const float* host, 
   memcpy(blobs[idx]->mutable_cpu_data(), host, sizeof(float) * count);
   return MSCNN_OK;
 }
+// host copy of a parameter blob (count must match)
+int mscnn_net_get_param(void* h, const char* layer, int idx, float* host, long count) {
+  if (!H(h)->net->has_layer(layer)) return MSCNN_ERR_INVALID;
+  auto& blobs = H(h)->net->layer_by_name(layer)->blobs();
+  if (idx < 0 || idx >= (int)blobs.size() || blobs[idx]->count() != count) return MSCNN_ERR_INVALID;
+  memcpy(host, blobs[idx]->cpu_data(), sizeof(float) * count);
+  return MSCNN_OK;
+}
 int mscnn_net_copy_trained(void* h, const char* caffemodel_path) {
   H(h)->net->CopyTrainedLayersFrom(std::string(caffemodel_path));
   return MSCNN_OK;

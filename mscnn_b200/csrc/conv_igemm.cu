@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mscnn_b200.h"
@@ -45,6 +46,7 @@ struct IgemmParams {
   int out_mode;    // MSCNN_OUT_NHWC_BF16, MSCNN_OUT_NCHW_F32 or MSCNN_OUT_NHWC_F32
   int has_lo_out;
   int stages, epi_bufs;
+  int fat;            // split mode with all four operand tiles (A_hi, A_lo, B_hi, B_lo) in one stage
   const float* bias;  // [Cout_pad]
   float* out_f32;     // NCHW fp32 (out_mode 1)
   int out_n, out_c, out_h, out_w;
@@ -75,9 +77,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
   const int S = p.stages;
+  const uint32_t a_stride = p.fat ? 2u * kABytes : kABytes;  // fat stage: [A_hi][A_lo]
+  const uint32_t b_stride = p.fat ? 2u * kBBytes : kBBytes;  //            [B_hi][B_lo]
   const uint32_t sA = smem_base;
-  const uint32_t sB = sA + S * kABytes;
-  const uint32_t sEpi = sB + S * kBBytes;  // 1024-aligned: kABytes, kBBytes are multiples of 1024
+  const uint32_t sB = sA + S * a_stride;
+  const uint32_t sEpi = sB + S * b_stride;  // 1024-aligned: kABytes, kBBytes are multiples of 1024
   const int epi_buf_bytes = kABytes * (p.has_lo_out ? 2 : 1);
   const uint32_t sMisc = sEpi + p.epi_bufs * epi_buf_bytes;
   uint8_t* misc_gen = smem_gen + (sMisc - smem_base);
@@ -127,7 +131,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   const int total_tiles = m_tiles * p.n_tiles;
-  const int num_kb = p.num_terms * p.taps_h * p.taps_w * p.cin_chunks;
+  const int num_kb = (p.fat ? 1 : p.num_terms) * p.taps_h * p.taps_w * p.cin_chunks;
   const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * kBlockK * 2;
 
   auto tile_coords = [&](int tile, int& n_tile, int& tw, int& th, int& tn) {
@@ -148,6 +152,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         int n_tile, tw, th, tn;
         tile_coords(tile, n_tile, tw, th, tn);
         const int w0 = tw * p.box_w - p.pad_w, h0 = th * p.box_h - p.pad_h, n0 = tn * p.box_n;
+        if (p.fat) {
+          // fp32-faithful mode, L2-traffic-lean form: one stage carries A_hi, A_lo, B_hi, B_lo of a
+          // (tap, channel chunk) and feeds three MMAs per K step, so A_hi / B_hi are fetched once.
+          for (int dy = 0; dy < p.taps_h; ++dy) {
+            for (int dx = 0; dx < p.taps_w; ++dx) {
+              const int tap = dy * p.taps_w + dx;
+              for (int cc = 0; cc < p.cin_chunks; ++cc) {
+                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+                ptx::mbar_expect_tx(full_bar(stage), 2u * a_box_bytes + 2u * kBBytes);
+                const uint32_t a0 = sA + stage * a_stride, b0 = sB + stage * b_stride;
+                const int kcol = (tap * p.cin_chunks + cc) * kBlockK;
+                ptx::tma_load_4d(a0, &tmA_hi, full_bar(stage), cc * kBlockK, w0 + dx, h0 + dy, n0);
+                ptx::tma_load_4d(a0 + kABytes, &tmA_lo, full_bar(stage), cc * kBlockK, w0 + dx, h0 + dy, n0);
+                ptx::tma_load_2d(b0, &tmB_hi, full_bar(stage), kcol, n_tile * BLOCK_N);
+                ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(stage), kcol, n_tile * BLOCK_N);
+                if (++stage == S) {
+                  stage = 0;
+                  phase ^= 1u;
+                }
+              }
+            }
+          }
+          continue;
+        }
         for (int term = 0; term < p.num_terms; ++term) {
           const CUtensorMap* mapA = (term == 2) ? &tmA_lo : &tmA_hi;
           const CUtensorMap* mapB = (term == 1) ? &tmB_lo : &tmB_hi;
@@ -157,9 +185,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
               for (int cc = 0; cc < p.cin_chunks; ++cc) {
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
                 ptx::mbar_expect_tx(full_bar(stage), a_box_bytes + kBBytes);
-                ptx::tma_load_4d(sA + stage * kABytes, mapA, full_bar(stage), cc * kBlockK,
+                ptx::tma_load_4d(sA + stage * a_stride, mapA, full_bar(stage), cc * kBlockK,
                                  w0 + dx, h0 + dy, n0);
-                ptx::tma_load_2d(sB + stage * kBBytes, mapB, full_bar(stage),
+                ptx::tma_load_2d(sB + stage * b_stride, mapB, full_bar(stage),
                                  (tap * p.cin_chunks + cc) * kBlockK, n_tile * BLOCK_N);
                 if (++stage == S) {
                   stage = 0;
@@ -185,13 +213,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint64_t a_desc = ptx::umma_desc_sw128(sA + stage * kABytes);
-          const uint64_t b_desc = ptx::umma_desc_sw128(sB + stage * kBBytes);
+          const uint64_t a_desc = ptx::umma_desc_sw128(sA + stage * a_stride);
+          const uint64_t b_desc = ptx::umma_desc_sw128(sB + stage * b_stride);
+          if (p.fat) {
+            const uint64_t a_lo = ptx::umma_desc_sw128(sA + stage * a_stride + kABytes);
+            const uint64_t b_lo = ptx::umma_desc_sw128(sB + stage * b_stride + kBBytes);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 B per UMMA_K step inside the 128 B swizzle atom -> +2 in the address field
-            ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc,
-                           (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_lo + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);  // hi * lo
+              ptx::umma_bf16(d_tmem, a_lo + 2u * k, b_desc + 2u * k, kIdesc, 1u);                        // lo * hi
+              ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);                      // hi * hi
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // +32 B per UMMA_K step inside the 128 B swizzle atom -> +2 in the address field
+              ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc,
+                             (kb | k) != 0 ? 1u : 0u);
+            }
           }
           ptx::umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs finish
           if (++stage == S) {
@@ -436,7 +475,9 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
 
   // shared memory plan
   const int b_bytes = BN * kBlockK * 2;
-  const int stage_bytes = kABytes + b_bytes;
+  // fat stages (all four operand tiles) for the L2-bound narrow-N layers of the fp32-faithful path
+  p.fat = (split && BN <= 128 && getenv("MSCNN_FAT")) ? 1 : 0;  // opt-in: measured slower on B200 (r01), kept for study
+  const int stage_bytes = (kABytes + b_bytes) * (p.fat ? 2 : 1);
   const int epi_unit = (d->out_mode == MSCNN_OUT_NHWC_BF16) ? kABytes * (p.has_lo_out ? 2 : 1) : 0;
   const int misc = BN * 4 + 8 * (2 * 8 + 4) + 16 + 1024 /*alignment slack*/;
   const int budget = 227 * 1024;

@@ -38,6 +38,7 @@ def _declare(L):
     L.mscnn_net_param_shape.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
     L.mscnn_net_set_param.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_long]
     L.mscnn_net_copy_trained.argtypes = [C.c_void_p, C.c_char_p]
+    L.mscnn_net_get_param.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_long]
     L.mscnn_net_blob_shape.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
     L.mscnn_net_reshape_blob.argtypes = [C.c_void_p, C.c_char_p] + [C.c_int] * 4
     L.mscnn_net_set_blob.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
@@ -125,6 +126,16 @@ class Net:
                 a = np.ascontiguousarray(b, dtype=np.float32)
                 capi.check(self._L.mscnn_net_set_param(self._h, name.encode(), i, a.ctypes.data, a.size),
                            f"set_param({name},{i})")
+
+    def param(self, layer: str, idx: int) -> np.ndarray:
+        shp = self.param_shapes(layer)[idx]
+        out = np.empty(shp, dtype=np.float32)
+        capi.check(self._L.mscnn_net_get_param(self._h, layer.encode(), idx, out.ctypes.data, out.size), "get_param")
+        return out
+
+    def param_checksums(self) -> dict[str, list[float]]:
+        return {n: [float(np.abs(self.param(n, i).astype(np.float64)).sum()) for i in range(len(sh))]
+                for n, _, sh in self.layers() if sh}
 
     def copy_from(self, caffemodel: str) -> None:
         capi.check(self._L.mscnn_net_copy_trained(self._h, str(caffemodel).encode()), "copy_trained")
