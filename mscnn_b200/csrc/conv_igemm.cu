@@ -47,6 +47,8 @@ struct IgemmParams {
   int has_lo_out;
   int stages, epi_bufs;
   int fat;            // split mode with all four operand tiles (A_hi, A_lo, B_hi, B_lo) in one stage
+  int mt;             // M sub-tiles (128 pixels each) per CTA tile: one weight tile feeds mt activation tiles
+  int tmem_cols;      // 2 * mt * BLOCK_N rounded to a power of two >= 32
   const float* bias;  // [Cout_pad]
   float* out_f32;     // NCHW fp32 (out_mode 1)
   int out_n, out_c, out_h, out_w;
@@ -59,6 +61,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
 constexpr int kThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kEpiBarId = 1;
+constexpr int kMaxMt = 4;
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -69,7 +72,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   const __grid_constant__ CUtensorMap tmO_hi,
                   const __grid_constant__ CUtensorMap tmO_lo, const IgemmParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  constexpr uint32_t kTmemCols = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // power of two for 32..256
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM, BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
@@ -77,8 +79,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
   const int S = p.stages;
-  const uint32_t a_stride = p.fat ? 2u * kABytes : kABytes;  // fat stage: [A_hi][A_lo]
-  const uint32_t b_stride = p.fat ? 2u * kBBytes : kBBytes;  //            [B_hi][B_lo]
+  const int MT = p.mt;
+  const uint32_t a_sub = p.fat ? 2u * kABytes : kABytes;     // one sub-tile: [A_hi] or [A_hi][A_lo]
+  const uint32_t a_stride = a_sub * MT;                      // one stage: MT sub-tiles
+  const uint32_t b_stride = p.fat ? 2u * kBBytes : kBBytes;  //            [B_hi] or [B_hi][B_lo]
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + S * a_stride;
   const uint32_t sEpi = sB + S * b_stride;  // 1024-aligned: kABytes, kBBytes are multiples of 1024
@@ -121,7 +125,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(sTmemPtr, kTmemCols);
+    ptx::tmem_alloc(sTmemPtr, static_cast<uint32_t>(p.tmem_cols));
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -130,13 +134,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = m_tiles * p.n_tiles;
+  const int total_tiles = (m_tiles / MT) * p.n_tiles;  // the host guarantees m_tiles % MT == 0
   const int num_kb = (p.fat ? 1 : p.num_terms) * p.taps_h * p.taps_w * p.cin_chunks;
   const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * kBlockK * 2;
+  const uint32_t stage_tx = (p.fat ? 2u : 1u) * (static_cast<uint32_t>(MT) * a_box_bytes + kBBytes);
 
-  auto tile_coords = [&](int tile, int& n_tile, int& tw, int& th, int& tn) {
-    n_tile = tile % p.n_tiles;
-    int m = tile / p.n_tiles;
+  // CTA tile -> n tile and first M sub-tile; M sub-tile -> pixel-box origin
+  auto m_coords = [&](int m, int& tw, int& th, int& tn) {
     tw = m % p.tiles_w;
     m /= p.tiles_w;
     th = m % p.tiles_h;
@@ -149,34 +153,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int n_tile, tw, th, tn;
-        tile_coords(tile, n_tile, tw, th, tn);
-        const int w0 = tw * p.box_w - p.pad_w, h0 = th * p.box_h - p.pad_h, n0 = tn * p.box_n;
-        if (p.fat) {
-          // fp32-faithful mode, L2-traffic-lean form: one stage carries A_hi, A_lo, B_hi, B_lo of a
-          // (tap, channel chunk) and feeds three MMAs per K step, so A_hi / B_hi are fetched once.
-          for (int dy = 0; dy < p.taps_h; ++dy) {
-            for (int dx = 0; dx < p.taps_w; ++dx) {
-              const int tap = dy * p.taps_w + dx;
-              for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                ptx::mbar_expect_tx(full_bar(stage), 2u * a_box_bytes + 2u * kBBytes);
-                const uint32_t a0 = sA + stage * a_stride, b0 = sB + stage * b_stride;
-                const int kcol = (tap * p.cin_chunks + cc) * kBlockK;
-                ptx::tma_load_4d(a0, &tmA_hi, full_bar(stage), cc * kBlockK, w0 + dx, h0 + dy, n0);
-                ptx::tma_load_4d(a0 + kABytes, &tmA_lo, full_bar(stage), cc * kBlockK, w0 + dx, h0 + dy, n0);
-                ptx::tma_load_2d(b0, &tmB_hi, full_bar(stage), kcol, n_tile * BLOCK_N);
-                ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(stage), kcol, n_tile * BLOCK_N);
-                if (++stage == S) {
-                  stage = 0;
-                  phase ^= 1u;
-                }
-              }
-            }
-          }
-          continue;
+        const int n_tile = tile % p.n_tiles, m0 = (tile / p.n_tiles) * MT;
+        int w0[kMaxMt], h0[kMaxMt], n0[kMaxMt];
+        for (int j = 0; j < MT; ++j) {
+          int tw, th, tn;
+          m_coords(m0 + j, tw, th, tn);
+          w0[j] = tw * p.box_w - p.pad_w;
+          h0[j] = th * p.box_h - p.pad_h;
+          n0[j] = tn * p.box_n;
         }
-        for (int term = 0; term < p.num_terms; ++term) {
+        const int terms = p.fat ? 1 : p.num_terms;
+        for (int term = 0; term < terms; ++term) {
           const CUtensorMap* mapA = (term == 2) ? &tmA_lo : &tmA_hi;
           const CUtensorMap* mapB = (term == 1) ? &tmB_lo : &tmB_hi;
           for (int dy = 0; dy < p.taps_h; ++dy) {
@@ -184,11 +171,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
               const int tap = dy * p.taps_w + dx;
               for (int cc = 0; cc < p.cin_chunks; ++cc) {
                 ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-                ptx::mbar_expect_tx(full_bar(stage), a_box_bytes + kBBytes);
-                ptx::tma_load_4d(sA + stage * a_stride, mapA, full_bar(stage), cc * kBlockK,
-                                 w0 + dx, h0 + dy, n0);
-                ptx::tma_load_2d(sB + stage * b_stride, mapB, full_bar(stage),
-                                 (tap * p.cin_chunks + cc) * kBlockK, n_tile * BLOCK_N);
+                ptx::mbar_expect_tx(full_bar(stage), stage_tx);
+                const uint32_t a0 = sA + stage * a_stride, b0 = sB + stage * b_stride;
+                const int kcol = (tap * p.cin_chunks + cc) * kBlockK;
+                ptx::tma_load_2d(b0, mapB, full_bar(stage), kcol, n_tile * BLOCK_N);
+                if (p.fat) ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(stage), kcol, n_tile * BLOCK_N);
+                for (int j = 0; j < MT; ++j) {
+                  ptx::tma_load_4d(a0 + j * a_sub, mapA, full_bar(stage), cc * kBlockK, w0[j] + dx, h0[j] + dy,
+                                   n0[j]);
+                  if (p.fat)
+                    ptx::tma_load_4d(a0 + j * a_sub + kABytes, &tmA_lo, full_bar(stage), cc * kBlockK, w0[j] + dx,
+                                     h0[j] + dy, n0[j]);
+                }
                 if (++stage == S) {
                   stage = 0;
                   phase ^= 1u;
@@ -209,27 +203,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * MT * BLOCK_N);
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
-          const uint64_t a_desc = ptx::umma_desc_sw128(sA + stage * a_stride);
           const uint64_t b_desc = ptx::umma_desc_sw128(sB + stage * b_stride);
-          if (p.fat) {
-            const uint64_t a_lo = ptx::umma_desc_sw128(sA + stage * a_stride + kABytes);
-            const uint64_t b_lo = ptx::umma_desc_sw128(sB + stage * b_stride + kBBytes);
+          const uint64_t b_lo = ptx::umma_desc_sw128(sB + stage * b_stride + kBBytes);
+          for (int j = 0; j < MT; ++j) {
+            const uint32_t d_tmem = d_base + static_cast<uint32_t>(j * BLOCK_N);
+            const uint64_t a_desc = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub);
+            if (p.fat) {
+              // three products per K step from one stage: hi*lo, lo*hi, hi*hi
+              const uint64_t a_lo = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub + kABytes);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_lo + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);  // hi * lo
-              ptx::umma_bf16(d_tmem, a_lo + 2u * k, b_desc + 2u * k, kIdesc, 1u);                        // lo * hi
-              ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);                      // hi * hi
-            }
-          } else {
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_lo + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                ptx::umma_bf16(d_tmem, a_lo + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+              }
+            } else {
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // +32 B per UMMA_K step inside the 128 B swizzle atom -> +2 in the address field
-              ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc,
-                             (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // +32 B per UMMA_K step inside the 128 B swizzle atom -> +2 in the address field
+                ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
           }
           ptx::umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs finish
@@ -238,7 +235,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
             phase ^= 1u;
           }
         }
-        ptx::umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        ptx::umma_commit(tfull_bar(acc));  // accumulators complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -254,121 +251,126 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     int ebuf = 0;
     const int hw_box = p.box_w * p.box_h;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int n_tile, tw, th, tn;
-      tile_coords(tile, n_tile, tw, th, tn);
+      const int n_tile = tile % p.n_tiles, m0 = (tile / p.n_tiles) * MT;
       const int n_base = n_tile * BLOCK_N;
       // bias slice for this n tile (visible after the first named barrier below)
       for (int j = et; j < BLOCK_N; j += kEpiThreads) bias_s[j] = p.bias[n_base + j];
 
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc * BLOCK_N) +
-                             (static_cast<uint32_t>(quarter * 32) << 16);
+      for (int sub = 0; sub < MT; ++sub) {
+        int tw, th, tn;
+        m_coords(m0 + sub, tw, th, tn);
+        const uint32_t t_row = tmem_base + static_cast<uint32_t>((acc * MT + sub) * BLOCK_N) +
+                               (static_cast<uint32_t>(quarter * 32) << 16);
 
-      if (p.out_mode == MSCNN_OUT_NHWC_BF16) {
-        if constexpr (BLOCK_N >= 64) {
+        if (p.out_mode == MSCNN_OUT_NHWC_BF16) {
+          if constexpr (BLOCK_N >= 64) {
 #pragma unroll 1
-          for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
-            uint32_t v[64];
-            ptx::tmem_ld_32x32(t_row + chunk * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-            ptx::tmem_ld_32x32(t_row + chunk * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-            // the staging buffer we are about to overwrite must have been read by its TMA store
-            if (issuer) {
-              if (p.epi_bufs == 1) ptx::tma_store_wait_read<0>();
-              else ptx::tma_store_wait_read<1>();
-            }
-            ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // also publishes bias_s
-            ptx::tmem_ld_wait();
-            const uint32_t buf = sEpi + ebuf * epi_buf_bytes;
-            const uint32_t row_hi = buf + row * 128;
-            const uint32_t row_lo = row_hi + kABytes;
+            for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
+              uint32_t v[64];
+              ptx::tmem_ld_32x32(t_row + chunk * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+              ptx::tmem_ld_32x32(t_row + chunk * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+              // the staging buffer we are about to overwrite must have been read by its TMA store
+              if (issuer) {
+                if (p.epi_bufs == 1) ptx::tma_store_wait_read<0>();
+                else ptx::tma_store_wait_read<1>();
+              }
+              ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // also publishes bias_s
+              ptx::tmem_ld_wait();
+              const uint32_t buf = sEpi + ebuf * epi_buf_bytes;
+              const uint32_t row_hi = buf + row * 128;
+              const uint32_t row_lo = row_hi + kABytes;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {  // 8 x 16 B = 64 channels
-              uint32_t hi[4], lo[4];
+              for (int j = 0; j < 8; ++j) {  // 8 x 16 B = 64 channels
+                uint32_t hi[4], lo[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                float f0 = __uint_as_float(v[j * 8 + 2 * q]) + bias_s[chunk * 64 + j * 8 + 2 * q];
-                float f1 =
-                    __uint_as_float(v[j * 8 + 2 * q + 1]) + bias_s[chunk * 64 + j * 8 + 2 * q + 1];
-                if (p.relu) {
-                  f0 = fmaxf(f0, 0.f);
-                  f1 = fmaxf(f1, 0.f);
+                for (int q = 0; q < 4; ++q) {
+                  float f0 = __uint_as_float(v[j * 8 + 2 * q]) + bias_s[chunk * 64 + j * 8 + 2 * q];
+                  float f1 =
+                      __uint_as_float(v[j * 8 + 2 * q + 1]) + bias_s[chunk * 64 + j * 8 + 2 * q + 1];
+                  if (p.relu) {
+                    f0 = fmaxf(f0, 0.f);
+                    f1 = fmaxf(f1, 0.f);
+                  }
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
+                  hi[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                          (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                  const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
+                  const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
+                  lo[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+                          (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
                 }
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
-                hi[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-                        (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
-                lo[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-                        (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-              }
-              const uint32_t off = static_cast<uint32_t>((j ^ (row & 7)) << 4);  // 128B swizzle
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off),
-                           "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
-                           : "memory");
-              if (p.has_lo_out)
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_lo + off),
-                             "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3])
+                const uint32_t off = static_cast<uint32_t>((j ^ (row & 7)) << 4);  // 128B swizzle
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off),
+                             "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3])
                              : "memory");
+                if (p.has_lo_out)
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_lo + off),
+                               "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3])
+                               : "memory");
+              }
+              ptx::fence_proxy_async_smem();
+              ptx::named_bar_sync(kEpiBarId, kEpiThreads);
+              if (issuer) {
+                const int c0 = n_base + chunk * 64;
+                ptx::tma_store_4d(&tmO_hi, buf, c0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+                if (p.has_lo_out)
+                  ptx::tma_store_4d(&tmO_lo, buf + kABytes, c0, tw * p.box_w, th * p.box_h,
+                                    tn * p.box_n);
+                ptx::tma_store_commit();
+              }
+              if (++ebuf == p.epi_bufs) ebuf = 0;
             }
-            ptx::fence_proxy_async_smem();
-            ptx::named_bar_sync(kEpiBarId, kEpiThreads);
-            if (issuer) {
-              const int c0 = n_base + chunk * 64;
-              ptx::tma_store_4d(&tmO_hi, buf, c0, tw * p.box_w, th * p.box_h, tn * p.box_n);
-              if (p.has_lo_out)
-                ptx::tma_store_4d(&tmO_lo, buf + kABytes, c0, tw * p.box_w, th * p.box_h,
-                                  tn * p.box_n);
-              ptx::tma_store_commit();
-            }
-            if (++ebuf == p.epi_bufs) ebuf = 0;
           }
-        }
-      } else {
-        // fp32 NCHW, direct stores: consecutive lanes are consecutive pixels of one channel.
-        ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // bias_s visible
-        const int dn = row / hw_box, rem = row - dn * hw_box;
-        const int dh = rem / p.box_w, dw = rem - dh * p.box_w;
-        const int n = tn * p.box_n + dn, h = th * p.box_h + dh, w = tw * p.box_w + dw;
-        const bool ok = (dn < p.box_n) && n < p.out_n && h < p.out_h && w < p.out_w;
-        const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
-        float* obase = p.out_f32 + (static_cast<size_t>(n) * p.out_c) * plane +
-                       static_cast<size_t>(h) * p.out_w + w;
-        // pixel-major fp32 rows [pixel][ld]: each thread owns one 128-byte segment per chunk
-        float* rbase = p.out_f32 + ((static_cast<size_t>(n) * p.out_h + h) * p.out_w + w) * p.out_ld + n_base;
+        } else {
+          // fp32 outputs, direct stores
+          if (sub == 0) ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // bias_s visible
+          const int dn = row / hw_box, rem = row - dn * hw_box;
+          const int dh = rem / p.box_w, dw = rem - dh * p.box_w;
+          const int n = tn * p.box_n + dn, h = th * p.box_h + dh, w = tw * p.box_w + dw;
+          const bool ok = (dn < p.box_n) && n < p.out_n && h < p.out_h && w < p.out_w;
+          const size_t plane = static_cast<size_t>(p.out_h) * p.out_w;
+          // NCHW: consecutive lanes are consecutive pixels of one channel
+          float* obase = p.out_f32 + (static_cast<size_t>(n) * p.out_c) * plane +
+                         static_cast<size_t>(h) * p.out_w + w;
+          // pixel-major fp32 rows [pixel][ld]: each thread owns one 128-byte segment per chunk
+          float* rbase = p.out_f32 + ((static_cast<size_t>(n) * p.out_h + h) * p.out_w + w) * p.out_ld + n_base;
 #pragma unroll 1
-        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32(t_row + chunk * 32, v);
-          ptx::tmem_ld_wait();
-          if (p.out_mode == MSCNN_OUT_NHWC_F32) {
-            if (ok) {
+          for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(t_row + chunk * 32, v);
+            ptx::tmem_ld_wait();
+            if (p.out_mode == MSCNN_OUT_NHWC_F32) {
+              if (ok) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                float4 o;
-                o.x = __uint_as_float(v[j]) + bias_s[chunk * 32 + j];
-                o.y = __uint_as_float(v[j + 1]) + bias_s[chunk * 32 + j + 1];
-                o.z = __uint_as_float(v[j + 2]) + bias_s[chunk * 32 + j + 2];
-                o.w = __uint_as_float(v[j + 3]) + bias_s[chunk * 32 + j + 3];
-                if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                *reinterpret_cast<float4*>(rbase + chunk * 32 + j) = o;
+                for (int j = 0; j < 32; j += 4) {
+                  float4 o;
+                  o.x = __uint_as_float(v[j]) + bias_s[chunk * 32 + j];
+                  o.y = __uint_as_float(v[j + 1]) + bias_s[chunk * 32 + j + 1];
+                  o.z = __uint_as_float(v[j + 2]) + bias_s[chunk * 32 + j + 2];
+                  o.w = __uint_as_float(v[j + 3]) + bias_s[chunk * 32 + j + 3];
+                  if (p.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                  *reinterpret_cast<float4*>(rbase + chunk * 32 + j) = o;
+                }
               }
-            }
-          } else if (ok) {
+            } else if (ok) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int ch = n_base + chunk * 32 + j;
-              if (ch < p.out_c) {
-                float f = __uint_as_float(v[j]) + bias_s[chunk * 32 + j];
-                if (p.relu) f = fmaxf(f, 0.f);
-                obase[static_cast<size_t>(ch) * plane] = f;
+              for (int j = 0; j < 32; ++j) {
+                const int ch = n_base + chunk * 32 + j;
+                if (ch < p.out_c) {
+                  float f = __uint_as_float(v[j]) + bias_s[chunk * 32 + j];
+                  if (p.relu) f = fmaxf(f, 0.f);
+                  obase[static_cast<size_t>(ch) * plane] = f;
+                }
               }
             }
           }
         }
-        ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // bias_s reuse hazard for the next tile
       }
-      // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
+      if (p.out_mode != MSCNN_OUT_NHWC_BF16)
+        ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // bias_s reuse hazard for the next tile
+      // all TMEM reads of these accumulators are done -> hand them back to the MMA warp
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty_bar(acc));
       acc ^= 1;
@@ -381,7 +383,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kTmemCols);
+    ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 }
 
@@ -475,23 +477,46 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
 
   // shared memory plan
   const int b_bytes = BN * kBlockK * 2;
-  // fat stages (all four operand tiles) for the L2-bound narrow-N layers of the fp32-faithful path
-  p.fat = (split && BN <= 128 && getenv("MSCNN_FAT")) ? 1 : 0;  // opt-in: measured slower on B200 (r01), kept for study
-  const int stage_bytes = (kABytes + b_bytes) * (p.fat ? 2 : 1);
+  // fat stages (all four operand tiles): opt-in, see profiles/r01_ncu_conv_summary.md
+  p.fat = (split && BN <= 128 && getenv("MSCNN_FAT")) ? 1 : 0;
+  // M sub-tiles per CTA tile: for narrow N one weight tile should feed several activation tiles
+  // (fewer hot-line weight fetches and barrier round trips per MMA).  2 * mt * BN TMEM columns <= 512.
+  const int m_tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
+  int mt = 1;
+  if (BN <= 64) mt = 4;
+  else if (BN == 128) mt = 2;
+  if (const char* e = getenv("MSCNN_MT")) mt = atoi(e);
+  if (mt > kMaxMt) mt = kMaxMt;
+  if (mt < 1) mt = 1;
+  while (mt > 1 && (2 * mt * BN > 512 || m_tiles_total % mt != 0 || m_tiles_total / mt * p.n_tiles < mscnn_sm_count())) mt >>= 1;
   const int epi_unit = (d->out_mode == MSCNN_OUT_NHWC_BF16) ? kABytes * (p.has_lo_out ? 2 : 1) : 0;
   const int misc = BN * 4 + 8 * (2 * 8 + 4) + 16 + 1024 /*alignment slack*/;
   const int budget = 227 * 1024;
   int epi_bufs = (epi_unit == 0) ? 0 : 2;
-  int stages = (budget - misc - epi_bufs * epi_unit) / stage_bytes;
-  if (stages < 4 && epi_bufs == 2) {
-    epi_bufs = 1;
+  int stage_bytes = 0, stages = 0;
+  for (;; mt >>= 1) {
+    stage_bytes = (mt * kABytes + b_bytes) * (p.fat ? 2 : 1);
+    epi_bufs = (epi_unit == 0) ? 0 : 2;
     stages = (budget - misc - epi_bufs * epi_unit) / stage_bytes;
+    if (stages < 4 && epi_bufs == 2) {
+      epi_bufs = 1;
+      stages = (budget - misc - epi_bufs * epi_unit) / stage_bytes;
+    }
+    if (stages >= 3 || mt == 1) break;  // keep at least a 3-deep TMA pipeline
   }
   if (stages > 8) stages = 8;
   if (stages < 2) return MSCNN_ERR_INVALID;
+  p.mt = mt;
+  int tcols = 32;
+  while (tcols < 2 * mt * BN) tcols <<= 1;
+  p.tmem_cols = tcols;
   p.stages = stages;
   p.epi_bufs = epi_bufs;  // 0 in fp32-output mode: no staging region is carved
   const size_t smem = (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
+  if (getenv("MSCNN_VERBOSE_CONV"))
+    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
+            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.num_terms, stages,
+            epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
   CUtensorMap maps[6];
   memset(maps, 0, sizeof(maps));
@@ -529,7 +554,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
     maps[5] = maps[0];
   }
 
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles;
+  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n / p.mt * p.n_tiles;
   int grid = mscnn_sm_count();
   if (grid > total_tiles) grid = total_tiles;
   cudaError_t e;

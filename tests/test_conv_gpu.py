@@ -50,6 +50,9 @@ CASES = [
     ("roi_c1_like",    7, 128, 7, 7, 128, 3, 0),
     ("conv1x1",        1, 64, 8, 24, 64, 1, 0),
     ("deepK",          1, 512, 6, 40, 128, 3, 1),
+    # enough M tiles that a CTA tile holds several 128-pixel sub-tiles (mt = 2 / 4 path)
+    ("mt_n64",         2, 64, 128, 160, 64, 3, 1),
+    ("mt_n128",        2, 64, 128, 320, 128, 3, 1),
 ]
 
 

@@ -45,14 +45,20 @@ def main():
         for split in (True, False):
             xp = ops.nchw_to_planes(xin, split)
             wp = ops.pack_conv_weights(wt, None, split)
+            msg = f"{name} split={split}:"
+            for mt in ("1", "2", "4"):
+                for fat in ((False, True) if split else (False,)):
+                    os.environ["MSCNN_MT"] = mt
+                    if fat:
+                        os.environ["MSCNN_FAT"] = "1"
+                    else:
+                        os.environ.pop("MSCNN_FAT", None)
+                    t = timeit(lambda: ops.conv_forward(xp, wp, 1, relu=True))
+                    msg += f"  mt{mt}{'+fat' if fat else ''} {t:.3f}"
             os.environ.pop("MSCNN_FAT", None)
+            os.environ.pop("MSCNN_MT", None)
             t = timeit(lambda: ops.conv_forward(xp, wp, 1, relu=True))
-            msg = f"{name} split={split}: {t:.3f} ms"
-            if split:
-                os.environ["MSCNN_FAT"] = "1"
-                t2 = timeit(lambda: ops.conv_forward(xp, wp, 1, relu=True))
-                os.environ.pop("MSCNN_FAT", None)
-                msg += f", fat {t2:.3f} ms"
+            msg += f"  default {t:.3f} ms"
             flops = 2.0 * B * cin * cout * 9 * h * w
             print(msg + f"  ({flops / t / 1e9:.0f} TFLOP/s algorithmic)", flush=True)
             del xp, wp
