@@ -93,20 +93,21 @@ __global__ void pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
 // ROIPoolingLayer::Forward_cpu (src/caffe/layers/roi_pooling_layer.cpp:49-139) including the
 // MS-CNN pad_ratio context extension (:66-72).  Output rows are written at channel offset
 // `c_off` of a [R][P][P][Cout_total] tensor, which fuses ConcatLayer (concat_layer.cpp:57-74).
+// One warp per (ROI, output bin): the bin geometry is computed once per warp (uniform), lanes
+// stride over the 8-channel groups so that every load / store is a 512-byte coalesced row segment.
 __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
                                 const float* __restrict__ rois, int R, int N, int H, int W, int C,
                                 int PH, int PW, float scale, float pad_ratio,
                                 __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
                                 int Ctot, int c_off) {
   const int cg = C / 8;
-  const size_t total = (size_t)R * PH * PW * cg;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int g = idx % cg;
-    size_t r = idx / cg;
-    const int pw = r % PW; r /= PW;
-    const int ph = r % PH;
-    const int roi = r / PH;
+  const int lane = threadIdx.x & 31;
+  const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
+  const size_t bins = (size_t)R * PH * PW;
+  for (size_t bin = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bin < bins; bin += warps_total) {
+    const int pw = bin % PW;
+    const int ph = (bin / PW) % PH;
+    const int roi = bin / ((size_t)PW * PH);
     const float* q = rois + (size_t)roi * 5;
     int b = (int)q[0];
     b = min(max(b, 0), N - 1);  // the reference CHECKs the range (:63-64); never out of range here
@@ -127,16 +128,18 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
     wstart = min(max(wstart + sw, 0), W);
     wend = min(max(wend + sw, 0), W);
     const bool empty = (hend <= hstart) || (wend <= wstart);
-    Vec8 best;
+    for (int g = lane; g < cg; g += 32) {
+      Vec8 best;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) best.v[i] = empty ? 0.f : -3.402823466e+38f;
-    for (int h = hstart; h < hend; ++h)
-      for (int w = wstart; w < wend; ++w) {
-        const Vec8 v = load8(xh, xl, ((size_t)(b * H + h) * W + w) * C + g * 8);
+      for (int i = 0; i < 8; ++i) best.v[i] = empty ? 0.f : -3.402823466e+38f;
+      for (int h = hstart; h < hend; ++h)
+        for (int w = wstart; w < wend; ++w) {
+          const Vec8 v = load8(xh, xl, ((size_t)(b * H + h) * W + w) * C + g * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) best.v[i] = (v.v[i] > best.v[i]) ? v.v[i] : best.v[i];
-      }
-    store8(yh, yl, ((size_t)(roi * PH + ph) * PW + pw) * Ctot + c_off + g * 8, best);
+          for (int i = 0; i < 8; ++i) best.v[i] = (v.v[i] > best.v[i]) ? v.v[i] : best.v[i];
+        }
+      store8(yh, yl, (size_t)bin * Ctot + c_off + g * 8, best);
+    }
   }
 }
 
@@ -263,7 +266,7 @@ extern "C" int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N,
       out_channels_total % 8 || out_channel_offset % 8 || out_channel_offset + C > out_channels_total)
     return MSCNN_ERR_INVALID;
   if (R == 0) return MSCNN_OK;
-  const size_t total = (size_t)R * pooled_h * pooled_w * (C / 8);
+  const size_t total = (size_t)R * pooled_h * pooled_w * 32;  // one warp per (ROI, bin)
   roi_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, rois, R, N, H, W, C, pooled_h, pooled_w,
       spatial_scale, pad_ratio, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total,
