@@ -149,44 +149,50 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles, m0 = (tile / p.n_tiles) * MT;
-        int w0[kMaxMt], h0[kMaxMt], n0[kMaxMt];
-        for (int j = 0; j < MT; ++j) {
-          int tw, th, tn;
-          m_coords(m0 + j, tw, th, tn);
-          w0[j] = tw * p.box_w - p.pad_w;
-          h0[j] = th * p.box_h - p.pad_h;
-          n0[j] = tn * p.box_n;
-        }
-        const int terms = p.fat ? 1 : p.num_terms;
-        for (int term = 0; term < terms; ++term) {
-          const CUtensorMap* mapA = (term == 2) ? &tmA_lo : &tmA_hi;
-          const CUtensorMap* mapB = (term == 1) ? &tmB_lo : &tmB_hi;
-          for (int dy = 0; dy < p.taps_h; ++dy) {
-            for (int dx = 0; dx < p.taps_w; ++dx) {
-              const int tap = dy * p.taps_w + dx;
-              for (int cc = 0; cc < p.cin_chunks; ++cc) {
-                ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+    // The whole warp walks the loops (warp-uniform control flow); one elected lane issues.
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles, m0 = (tile / p.n_tiles) * MT;
+      int w0[kMaxMt], h0[kMaxMt], n0[kMaxMt];
+#pragma unroll
+      for (int j = 0; j < kMaxMt; ++j) {
+        int tw, th, tn;
+        m_coords(m0 + (j < MT ? j : 0), tw, th, tn);
+        w0[j] = tw * p.box_w - p.pad_w;
+        h0[j] = th * p.box_h - p.pad_h;
+        n0[j] = tn * p.box_n;
+      }
+      const int terms = p.fat ? 1 : p.num_terms;
+      for (int term = 0; term < terms; ++term) {
+        const CUtensorMap* mapA = (term == 2) ? &tmA_lo : &tmA_hi;
+        const CUtensorMap* mapB = (term == 1) ? &tmB_lo : &tmB_hi;
+        for (int dy = 0; dy < p.taps_h; ++dy) {
+          for (int dx = 0; dx < p.taps_w; ++dx) {
+            const int tap = dy * p.taps_w + dx;
+            for (int cc = 0; cc < p.cin_chunks; ++cc) {
+              ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+              if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(full_bar(stage), stage_tx);
                 const uint32_t a0 = sA + stage * a_stride, b0 = sB + stage * b_stride;
                 const int kcol = (tap * p.cin_chunks + cc) * kBlockK;
                 ptx::tma_load_2d(b0, mapB, full_bar(stage), kcol, n_tile * BLOCK_N);
                 if (p.fat) ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(stage), kcol, n_tile * BLOCK_N);
-                for (int j = 0; j < MT; ++j) {
-                  ptx::tma_load_4d(a0 + j * a_sub, mapA, full_bar(stage), cc * kBlockK, w0[j] + dx, h0[j] + dy,
-                                   n0[j]);
-                  if (p.fat)
-                    ptx::tma_load_4d(a0 + j * a_sub + kABytes, &tmA_lo, full_bar(stage), cc * kBlockK, w0[j] + dx,
-                                     h0[j] + dy, n0[j]);
+#pragma unroll
+                for (int j = 0; j < kMaxMt; ++j) {
+                  if (j < MT) {
+                    ptx::tma_load_4d(a0 + j * a_sub, mapA, full_bar(stage), cc * kBlockK, w0[j] + dx, h0[j] + dy,
+                                     n0[j]);
+                    if (p.fat)
+                      ptx::tma_load_4d(a0 + j * a_sub + kABytes, &tmA_lo, full_bar(stage), cc * kBlockK,
+                                       w0[j] + dx, h0[j] + dy, n0[j]);
+                  }
                 }
-                if (++stage == S) {
-                  stage = 0;
-                  phase ^= 1u;
-                }
+              }
+              __syncwarp();
+              if (++stage == S) {
+                stage = 0;
+                phase ^= 1u;
               }
             }
           }
@@ -195,50 +201,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * MT * BLOCK_N);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
-        const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * MT * BLOCK_N);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(full_bar(stage), phase);
-          ptx::tc_fence_after();
+        if (ptx::elect_one()) {
           const uint64_t b_desc = ptx::umma_desc_sw128(sB + stage * b_stride);
           const uint64_t b_lo = ptx::umma_desc_sw128(sB + stage * b_stride + kBBytes);
-          for (int j = 0; j < MT; ++j) {
-            const uint32_t d_tmem = d_base + static_cast<uint32_t>(j * BLOCK_N);
-            const uint64_t a_desc = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub);
-            if (p.fat) {
-              // three products per K step from one stage: hi*lo, lo*hi, hi*hi
-              const uint64_t a_lo = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub + kABytes);
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_lo + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
-                ptx::umma_bf16(d_tmem, a_lo + 2u * k, b_desc + 2u * k, kIdesc, 1u);
-                ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
-              }
-            } else {
+          for (int j = 0; j < kMaxMt; ++j) {
+            if (j < MT) {
+              const uint32_t d_tmem = d_base + static_cast<uint32_t>(j * BLOCK_N);
+              const uint64_t a_desc = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub);
+              if (p.fat) {
+                // three products per K step from one stage: hi*lo, lo*hi, hi*hi
+                const uint64_t a_lo = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub + kABytes);
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                // +32 B per UMMA_K step inside the 128 B swizzle atom -> +2 in the address field
-                ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_lo + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                  ptx::umma_bf16(d_tmem, a_lo + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                  ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  // +32 B per UMMA_K step inside the 128 B swizzle atom -> +2 in the address field
+                  ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+                }
               }
             }
           }
           ptx::umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs finish
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          if (kb == num_kb - 1) ptx::umma_commit(tfull_bar(acc));  // accumulators complete -> epilogue
         }
-        ptx::umma_commit(tfull_bar(acc));  // accumulators complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else {
     // ---------------------------------------------------------------- epilogue

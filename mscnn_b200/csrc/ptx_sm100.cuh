@@ -169,6 +169,19 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
          | (static_cast<uint32_t>(M >> 4) << 24);  // M / 16
 }
 
+// One lane of a CONVERGED warp (the lowest): lets single-thread instructions (TMA, tcgen05.mma,
+// tcgen05.commit) be issued from warp-uniform code, so that their operands live in uniform registers
+// without the per-instruction "waterfall" loop a divergent `if (lane == 0)` branch forces.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
