@@ -299,7 +299,8 @@ def main() -> None:
         flops, conv_launches = conv_flops(net, B)
         results[mode] = dict(ms=ms, ms_e2e=ms_e2e, props=float(props.item()), conv_ms=conv_ms, all_ms=all_ms,
                              flops=flops, conv_launches=conv_launches, clocks=clocks,
-                             top=sorted(((min(lt[k], lt2[k]), k) for k in lt), reverse=True)[:6])
+                             top=sorted(((min(lt[k], lt2[k]), k) for k in lt), reverse=True)[:6],
+                             layers={k: round(min(lt[k], lt2[k]), 3) for k in lt if min(lt[k], lt2[k]) >= 0.02})
     mnet.set_precision("fp32")
 
     if rank != 0:
@@ -342,6 +343,7 @@ def main() -> None:
                             "(two timed forwards after the timed region, min per layer, same stream)"},
         "clocks": r["clocks"],
         "top_layers_ms": [[k, round(v, 3)] for v, k in r["top"]],
+        "layers_ms": r["layers"],
     }
     if "bf16" in results:
         b = results["bf16"]
@@ -352,7 +354,7 @@ def main() -> None:
                         "note": "plain bf16 conv path: fails the 1e-3 parity gate (bf16 rounding of activations), "
                                 "reported as BASELINE.json config 3 asks; proposals/image differ accordingly",
                         "proposals_per_image": b["props"] / (B * world),
-                        "top_layers_ms": [[k, round(v, 3)] for v, k in b["top"]]}
+                        "top_layers_ms": [[k, round(v, 3)] for v, k in b["top"]], "layers_ms": b["layers"]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
