@@ -196,6 +196,13 @@ MSCNN_API int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N, 
                            float pad_ratio, void* y_hi, void* y_lo, int out_channels_total,
                            int out_channel_offset, void* stream);
 
+/* Same, for up to 4 pad_ratio variants of one ROI set in a single launch (MS-CNN's object + context
+ * pooling): variant i is written at channel offset out_channel_offsets[i] of y. */
+MSCNN_API int mscnn_roi_pool_multi_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                 const float* rois, int R, int pooled_h, int pooled_w, float spatial_scale,
+                                 int num_variants, const float* pad_ratios, const int* out_channel_offsets,
+                                 void* y_hi, void* y_lo, int out_channels_total, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Final detections for one class: softmax probability, bbox-delta decode, clip, greedy NMS.
  * Replaces the MATLAB code after net.forward in the reference driver

@@ -232,12 +232,29 @@ class ROIPoolingLayer : public Layer<Dtype> {
   void set_concat_target(Blob<Dtype>* target, int channel_offset, int total_channels) {
     concat_top_ = target; concat_offset_ = channel_offset; concat_channels_ = total_channels;
   }
+  // mscnn_b200 extension (set by Net): the sibling ROIPooling layers that feed the same Concat.  The
+  // first one pools all siblings that read the same feature map / ROIs in ONE launch; the others
+  // then find their work done (done_by_leader_) and return.
+  struct Sibling {
+    ROIPoolingLayer<Dtype>* layer;
+    Blob<Dtype>* feature;
+    Blob<Dtype>* rois;
+  };
+  void set_siblings(const vector<Sibling>& s) { siblings_ = s; }
+  float pad_ratio() const { return pad_ratio_; }
+  float spatial_scale() const { return spatial_scale_; }
+  int pooled_h() const { return pooled_height_; }
+  int pooled_w() const { return pooled_width_; }
+  int concat_offset() const { return concat_offset_; }
+  void mark_done_by_leader() { done_by_leader_ = true; }
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
   int channels_, height_, width_, pooled_height_, pooled_width_;
   float spatial_scale_, pad_ratio_;
   Blob<Dtype>* concat_top_;
   int concat_offset_, concat_channels_;
+  vector<Sibling> siblings_;
+  bool done_by_leader_ = false;
 };
 
 }  // namespace caffe

@@ -613,6 +613,10 @@ void ROIPoolingLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, const v
 }
 template <typename Dtype>
 void ROIPoolingLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  if (done_by_leader_) {  // a sibling already pooled this variant in its launch
+    done_by_leader_ = false;
+    return;
+  }
   const bool split = Caffe::split();
   typename Blob<Dtype>::Planes x = bottom[0]->planes(split);
   const int R = bottom[1]->num();
@@ -621,9 +625,26 @@ void ROIPoolingLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, con
     // fused ConcatLayer: the Net sized concat_top_ as [R, total, ph, pw]
     concat_top_->Reshape(R, concat_channels_, pooled_height_, pooled_width_);
     typename Blob<Dtype>::Planes y = concat_top_->mutable_planes(split);
-    MSCNN_CHECK(mscnn_roi_pool_forward(x.hi, x.lo, x.n, x.h, x.w, x.cpad, rois, R, pooled_height_, pooled_width_,
-                                       spatial_scale_, pad_ratio_, y.hi, y.lo, y.cpad, concat_offset_,
-                                       Caffe::stream()));
+    float ratios[4];
+    int offs[4];
+    int nv = 0;
+    ratios[nv] = pad_ratio_;
+    offs[nv++] = concat_offset_;
+    for (size_t i = 0; i < siblings_.size() && nv < 4; ++i) {
+      ROIPoolingLayer<Dtype>* sb = siblings_[i].layer;
+      if (sb == this) continue;
+      // same feature map (shared through Split), same ROIs, same geometry -> same launch
+      typename Blob<Dtype>::Planes sx = siblings_[i].feature->planes(split);
+      if (sx.hi == x.hi && siblings_[i].rois->gpu_data() == rois && sb->pooled_h() == pooled_height_ &&
+          sb->pooled_w() == pooled_width_ && sb->spatial_scale() == spatial_scale_) {
+        ratios[nv] = sb->pad_ratio();
+        offs[nv++] = sb->concat_offset();
+        sb->mark_done_by_leader();
+      }
+    }
+    MSCNN_CHECK(mscnn_roi_pool_multi_forward(x.hi, x.lo, x.n, x.h, x.w, x.cpad, rois, R, pooled_height_,
+                                             pooled_width_, spatial_scale_, nv, ratios, offs, y.hi, y.lo, y.cpad,
+                                             Caffe::stream()));
   } else {
     typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
     MSCNN_CHECK(mscnn_roi_pool_forward(x.hi, x.lo, x.n, x.h, x.w, x.cpad, rois, R, pooled_height_, pooled_width_,

@@ -228,10 +228,19 @@ void Net<Dtype>::FuseLayers() {
     }
     if (!ok) continue;
     int off = 0;
+    vector<typename ROIPoolingLayer<Dtype>::Sibling> sibs;
     for (size_t b = 0; b < producers.size(); ++b) {
       producers[b]->set_concat_target(top_vecs_[i][0], off, total);
       off += bottom_vecs_[i][b]->channels();
     }
+    for (int k = 0; k < L; ++k)  // execution order
+      for (size_t b = 0; b < producers.size(); ++b)
+        if (layers_[k].get() == producers[b]) {
+          typename ROIPoolingLayer<Dtype>::Sibling sb = {producers[b], bottom_vecs_[k][0], bottom_vecs_[k][1]};
+          sibs.push_back(sb);
+        }
+    // only the FIRST producer in execution order leads; it needs every sibling's inputs
+    if (!sibs.empty()) sibs[0].layer->set_siblings(sibs);
     cat->set_fused(true);
   }
 }

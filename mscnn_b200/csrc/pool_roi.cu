@@ -95,11 +95,19 @@ __global__ void pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
 // `c_off` of a [R][P][P][Cout_total] tensor, which fuses ConcatLayer (concat_layer.cpp:57-74).
 // One warp per (ROI, output bin): the bin geometry is computed once per warp (uniform), lanes
 // stride over the 8-channel groups so that every load / store is a 512-byte coalesced row segment.
+// Up to four pad_ratio variants of the same ROI set are pooled by the same warp (MS-CNN pools every
+// ROI twice, object and 1.5x context window, and concatenates): the context window contains the
+// object window, so the second variant mostly hits lines the first one just touched.
+struct RoiVariants {
+  int count;
+  float pad_ratio[4];
+  int c_off[4];
+};
+
 __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
                                 const float* __restrict__ rois, int R, int N, int H, int W, int C,
-                                int PH, int PW, float scale, float pad_ratio,
-                                __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl,
-                                int Ctot, int c_off) {
+                                int PH, int PW, float scale, const RoiVariants var,
+                                __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int Ctot) {
   const int cg = C / 8;
   const int lane = threadIdx.x & 31;
   const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
@@ -111,34 +119,49 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
     const float* q = rois + (size_t)roi * 5;
     int b = (int)q[0];
     b = min(max(b, 0), N - 1);  // the reference CHECKs the range (:63-64); never out of range here
-    const float pad_w = (q[3] - q[1] + 1.f) * pad_ratio;
-    const float pad_h = (q[4] - q[2] + 1.f) * pad_ratio;
-    const int sw = (int)roundf((q[1] - pad_w) * scale);
-    const int sh = (int)roundf((q[2] - pad_h) * scale);
-    const int ew = (int)roundf((q[3] + pad_w) * scale);
-    const int eh = (int)roundf((q[4] + pad_h) * scale);
-    const int roi_h = max(eh - sh + 1, 1), roi_w = max(ew - sw + 1, 1);
-    const float bin_h = (float)roi_h / (float)PH, bin_w = (float)roi_w / (float)PW;
-    int hstart = (int)floorf((float)ph * bin_h);
-    int wstart = (int)floorf((float)pw * bin_w);
-    int hend = (int)ceilf((float)(ph + 1) * bin_h);
-    int wend = (int)ceilf((float)(pw + 1) * bin_w);
-    hstart = min(max(hstart + sh, 0), H);
-    hend = min(max(hend + sh, 0), H);
-    wstart = min(max(wstart + sw, 0), W);
-    wend = min(max(wend + sw, 0), W);
-    const bool empty = (hend <= hstart) || (wend <= wstart);
-    for (int g = lane; g < cg; g += 32) {
-      Vec8 best;
+    const float q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];
+    for (int vi = 0; vi < var.count; ++vi) {
+      const float pad_w = (q3 - q1 + 1.f) * var.pad_ratio[vi];
+      const float pad_h = (q4 - q2 + 1.f) * var.pad_ratio[vi];
+      const int sw = (int)roundf((q1 - pad_w) * scale);
+      const int sh = (int)roundf((q2 - pad_h) * scale);
+      const int ew = (int)roundf((q3 + pad_w) * scale);
+      const int eh = (int)roundf((q4 + pad_h) * scale);
+      const int roi_h = max(eh - sh + 1, 1), roi_w = max(ew - sw + 1, 1);
+      const float bin_h = (float)roi_h / (float)PH, bin_w = (float)roi_w / (float)PW;
+      int hstart = (int)floorf((float)ph * bin_h);
+      int wstart = (int)floorf((float)pw * bin_w);
+      int hend = (int)ceilf((float)(ph + 1) * bin_h);
+      int wend = (int)ceilf((float)(pw + 1) * bin_w);
+      hstart = min(max(hstart + sh, 0), H);
+      hend = min(max(hend + sh, 0), H);
+      wstart = min(max(wstart + sw, 0), W);
+      wend = min(max(wend + sw, 0), W);
+      const bool empty = (hend <= hstart) || (wend <= wstart);
+      for (int g = lane; g < cg; g += 32) {
+        Vec8 best;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) best.v[i] = empty ? 0.f : -3.402823466e+38f;
-      for (int h = hstart; h < hend; ++h)
-        for (int w = wstart; w < wend; ++w) {
-          const Vec8 v = load8(xh, xl, ((size_t)(b * H + h) * W + w) * C + g * 8);
+        for (int i = 0; i < 8; ++i) best.v[i] = empty ? 0.f : -3.402823466e+38f;
+        for (int h = hstart; h < hend; ++h) {
+          const size_t rowbase = ((size_t)(b * H + h) * W) * C + g * 8;
+          int w = wstart;
+          for (; w + 1 < wend; w += 2) {  // two independent loads in flight
+            const Vec8 v0 = load8(xh, xl, rowbase + (size_t)w * C);
+            const Vec8 v1 = load8(xh, xl, rowbase + (size_t)(w + 1) * C);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) best.v[i] = (v.v[i] > best.v[i]) ? v.v[i] : best.v[i];
+            for (int i = 0; i < 8; ++i) {
+              best.v[i] = (v0.v[i] > best.v[i]) ? v0.v[i] : best.v[i];
+              best.v[i] = (v1.v[i] > best.v[i]) ? v1.v[i] : best.v[i];
+            }
+          }
+          if (w < wend) {
+            const Vec8 v0 = load8(xh, xl, rowbase + (size_t)w * C);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) best.v[i] = (v0.v[i] > best.v[i]) ? v0.v[i] : best.v[i];
+          }
         }
-      store8(yh, yl, (size_t)bin * Ctot + c_off + g * 8, best);
+        store8(yh, yl, (size_t)bin * Ctot + var.c_off[vi] + g * 8, best);
+      }
     }
   }
 }
@@ -258,20 +281,35 @@ extern "C" int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi
   return launch_check("pool");
 }
 
-extern "C" int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
-                                      const float* rois, int R, int pooled_h, int pooled_w,
-                                      float spatial_scale, float pad_ratio, void* y_hi, void* y_lo,
-                                      int out_channels_total, int out_channel_offset, void* stream) {
-  if (!x_hi || !y_hi || !rois || N <= 0 || C % 8 || R < 0 || pooled_h <= 0 || pooled_w <= 0 ||
-      out_channels_total % 8 || out_channel_offset % 8 || out_channel_offset + C > out_channels_total)
+extern "C" int mscnn_roi_pool_multi_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                            const float* rois, int R, int pooled_h, int pooled_w,
+                                            float spatial_scale, int num_variants, const float* pad_ratios,
+                                            const int* out_channel_offsets, void* y_hi, void* y_lo,
+                                            int out_channels_total, void* stream) {
+  if (!x_hi || !y_hi || !rois || !pad_ratios || !out_channel_offsets || N <= 0 || C % 8 || R < 0 ||
+      pooled_h <= 0 || pooled_w <= 0 || out_channels_total % 8 || num_variants < 1 || num_variants > 4)
     return MSCNN_ERR_INVALID;
+  RoiVariants var;
+  var.count = num_variants;
+  for (int i = 0; i < num_variants; ++i) {
+    if (out_channel_offsets[i] % 8 || out_channel_offsets[i] + C > out_channels_total) return MSCNN_ERR_INVALID;
+    var.pad_ratio[i] = pad_ratios[i];
+    var.c_off[i] = out_channel_offsets[i];
+  }
   if (R == 0) return MSCNN_OK;
   const size_t total = (size_t)R * pooled_h * pooled_w * 32;  // one warp per (ROI, bin)
   roi_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, rois, R, N, H, W, C, pooled_h, pooled_w,
-      spatial_scale, pad_ratio, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total,
-      out_channel_offset);
+      spatial_scale, var, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total);
   return launch_check("roi_pool");
+}
+
+extern "C" int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                      const float* rois, int R, int pooled_h, int pooled_w,
+                                      float spatial_scale, float pad_ratio, void* y_hi, void* y_lo,
+                                      int out_channels_total, int out_channel_offset, void* stream) {
+  return mscnn_roi_pool_multi_forward(x_hi, x_lo, N, H, W, C, rois, R, pooled_h, pooled_w, spatial_scale, 1,
+                                      &pad_ratio, &out_channel_offset, y_hi, y_lo, out_channels_total, stream);
 }
 
 extern "C" int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const float* w, void* y_hi,
