@@ -109,14 +109,17 @@ MSCNN_API int mscnn_pack_fc_weights(const float* w_f32, void* w_hi, void* w_lo, 
 MSCNN_API int mscnn_conv3x3_c3_forward(const float* x, const float* w, const float* bias, void* y_hi, void* y_lo,
                              int N, int H, int W, int Cout, int Cout_pad, int relu, void* stream);
 
-/* Narrow-output k x k heads (LFCN_*: Cout = 9, k = 5 / 7) as ONE 1x1 GEMM plus a gather.
- * A k x k conv with tiny Cout wastes the tensor core (N = 16..32) and re-reads the activation tile
- * once per tap; instead taps move into the GEMM's N dimension:
- *   P[pixel][tap*Cout + co] = sum_c x[pixel][c] * w[co][c][tap]        (mscnn_conv_forward, 1x1,
- *                                                                        MSCNN_OUT_NHWC_F32, N = k*k*Cout)
- *   y[n][co][h][w] = bias[co] + sum_tap P[(n, h+dy-pad, w+dx-pad)][tap*Cout + co]   (mscnn_head_gather)
- * Same FLOPs as the convolution, the activation is read once, summation order differs from
- * im2col+sgemm only in fp32 rounding.  Replaces ConvolutionLayer::Forward_gpu for those layers. */
+/* Narrow-output k x k heads (LFCN_*: Cout = 9, k = 5 / 7).  A direct k x k conv with tiny Cout
+ * wastes the tensor core (N = 16..32) and re-reads the activation tile once per tap.  Instead the
+ * horizontal taps move into the GEMM's N dimension and only the vertical taps stay in K:
+ *   P[pixel][dx*Cout + co] = sum_dy sum_c x[pixel + dy - pad rows][c] * w[co][c][dy][dx]
+ *                            (mscnn_conv_forward as a k x 1 conv, pad_w = 0, N = k*Cout -> 64,
+ *                             MSCNN_OUT_NHWC_F32)
+ *   y[n][co][h][w] = bias[co] + sum_dx P[(n, h, w + dx - pad)][dx*Cout + co]   (mscnn_head_gather)
+ * Same FLOPs as the convolution, k instead of k*k activation reads, a 64-column fp32 intermediate;
+ * the summation order differs from im2col+sgemm only in fp32 rounding.  Replaces
+ * ConvolutionLayer::Forward_gpu for those layers.  mscnn_pack_head_weights writes planes
+ * [N_pad][k][1][Cin_pad] with row n = dx*Cout + co. */
 MSCNN_API int mscnn_pack_head_weights(const float* w_f32 /*[Cout][Cin][k][k]*/, void* w_hi, void* w_lo, int Cout,
                             int Cin, int k, int N_pad, int Cin_pad, void* stream);
 MSCNN_API int mscnn_head_gather(const float* P, int ld, const float* bias, float* y /*[N][Cout][H][W]*/, int N, int H,
@@ -131,6 +134,15 @@ MSCNN_API int mscnn_planes_to_nchw_f32(const void* hi, const void* lo, float* y,
  * channel k = c*9 + dy*3 + dx for k < 27 (Caffe's own weight order), zero above. */
 MSCNN_API int mscnn_im2col3x3_c3_to_planes(const float* x, void* hi, void* lo, int N, int H, int W,
                                  void* stream);
+
+/* conv1_1 on the tensor cores with the 64-wide k-block fully used: one GEMM row = two horizontally
+ * adjacent pixels (54 of 64 channels = 2 x 27 taps); with the block-diagonal weights
+ * [2*Cout_pad][64] from mscnn_pack_conv1_pair_weights, mscnn_conv_forward (1x1, Cout = 2*Cout_pad) on
+ * the [N][H][W/2][64] patch planes writes exactly the NHWC tensor [N][H][W][Cout_pad].  W must be even. */
+MSCNN_API int mscnn_im2col3x3_c3_pair_to_planes(const float* x, void* hi, void* lo, int N, int H, int W,
+                                      void* stream);
+MSCNN_API int mscnn_pack_conv1_pair_weights(const float* w_f32 /*[Cout][3][3][3]*/, void* w_hi, void* w_lo, int Cout,
+                                  int Cout_pad, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Pooling, pad 0, ceil-mode output size.  Replaces PoolingLayer::Forward_gpu

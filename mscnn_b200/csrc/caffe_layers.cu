@@ -2,6 +2,7 @@
 // reference layer sources (cited per method); the arithmetic is delegated to the C ABI.
 #include <cstring>
 #include <random>
+#include <string>
 
 #include "caffe/layers/mscnn_layers.hpp"
 
@@ -157,17 +158,17 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
   Blob<Dtype>* bias = bias_term_ ? this->blobs_[1].get() : nullptr;
   mscnn_conv_desc d;
   memset(&d, 0, sizeof(d));
-  // Narrow k x k proposal heads (LFCN_*: 9 or 6 outputs, 5x5 / 7x7, "same" padding): taps move
-  // into the GEMM's N dimension and a gather sums them (see mscnn_head_gather in the C ABI).
+  // Narrow k x k proposal heads (LFCN_*: 9 or 6 outputs, 5x5 / 7x7, "same" padding): the horizontal
+  // taps move into the GEMM's N dimension and a 1-D gather sums them (mscnn_head_gather in the C ABI).
   const bool head_path = (num_output_ == 9 || num_output_ == 6) && kernel_h_ == kernel_w_ && kernel_h_ > 1 &&
                          pad_h_ == pad_w_ && 2 * pad_h_ + 1 == kernel_h_ && !fuse_relu_ && channels_ % 64 == 0 &&
                          !std::getenv("MSCNN_NO_HEAD_TAPS");
   if (head_path) {
-    const int k = kernel_h_, taps = k * k;
-    const int n_pad = (taps * num_output_ + 255) / 256 * 256;
+    const int k = kernel_h_;
+    const int n_pad = (k * num_output_ + 63) / 64 * 64;
     Blob<Dtype>* wb = this->blobs_[0].get();
     if (packed_.w_version != wb->version() || packed_.split != split || packed_.cout_pad != n_pad) {
-      packed_.w.reserve((size_t)n_pad * channels_ * 2, split);
+      packed_.w.reserve((size_t)n_pad * k * channels_ * 2, split);
       MSCNN_CHECK(mscnn_pack_head_weights(wb->gpu_data(), packed_.w.hi, split ? packed_.w.lo : nullptr, num_output_,
                                           channels_, k, n_pad, channels_, Caffe::stream()));
       if (packed_.bias) CUDA_CHECK(cudaFree(packed_.bias));
@@ -193,8 +194,9 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
     d.w_hi = packed_.w.hi; d.w_lo = split ? packed_.w.lo : nullptr;
     d.bias = packed_.bias;
     d.Cout = n_pad; d.Cout_pad = n_pad;
-    d.KH = d.KW = 1;
-    d.out_mode = MSCNN_OUT_NHWC_F32;
+    d.KH = k; d.KW = 1;        // vertical taps stay in K ...
+    d.pad_h = pad_h_; d.pad_w = 0;
+    d.out_mode = MSCNN_OUT_NHWC_F32;  // ... horizontal taps are columns of P
     d.y_f32 = P;
     MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
     MSCNN_CHECK(mscnn_head_gather(P, n_pad, head_bias_, top[0]->mutable_gpu_data(), N, H, W, num_output_, k, pad_h_,
@@ -204,14 +206,62 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
   // conv1_1-style layer (3 input channels, 3x3, pad 1): K = 27 is far below one 64-channel
   // tensor-core k-block; it runs as a direct exact-fp32 kernel straight from the NCHW input blob.
   const bool first_path = (channels_ == 3 && kernel_h_ == 3 && kernel_w_ == 3 && pad_h_ == 1 && pad_w_ == 1);
-  if (first_path && !std::getenv("MSCNN_CONV1_GEMM")) {
+  const char* conv1_mode = std::getenv("MSCNN_CONV1");  // "direct" | "patch" | default = pixel-pair GEMM
+  if (first_path && (W % 2 == 0) && num_output_ % 64 == 0 && !conv1_mode) {
+    // Pixel-pair GEMM: rows = two adjacent pixels (K = 54 of 64), block-diagonal weights, the output
+    // [N][H][W/2][2*Cout] is the NHWC tensor [N][H][W][Cout] (see mscnn_im2col3x3_c3_pair_to_planes).
+    const int cp = num_output_;  // multiple of 64
+    Blob<Dtype>* wb = this->blobs_[0].get();
+    if (packed_.w_version != wb->version() || packed_.split != split || packed_.cout_pad != 2 * cp) {
+      packed_.w.reserve((size_t)2 * cp * 64 * 2, split);
+      MSCNN_CHECK(mscnn_pack_conv1_pair_weights(wb->gpu_data(), packed_.w.hi, split ? packed_.w.lo : nullptr,
+                                                num_output_, cp, Caffe::stream()));
+      packed_.w_version = wb->version();
+      packed_.split = split;
+      packed_.b_version = ~0ul;
+      if (packed_.bias) { CUDA_CHECK(cudaFree(packed_.bias)); packed_.bias = nullptr; }
+    }
+    const unsigned long bver = bias ? bias->version() : 0;
+    if (!packed_.bias || packed_.b_version != bver) {
+      if (!packed_.bias) CUDA_CHECK(cudaMalloc(&packed_.bias, sizeof(float) * 2 * cp));
+      CUDA_CHECK(cudaMemsetAsync(packed_.bias, 0, sizeof(float) * 2 * cp, Caffe::stream()));
+      if (bias) {
+        CUDA_CHECK(cudaMemcpyAsync(packed_.bias, bias->gpu_data(), sizeof(float) * num_output_,
+                                   cudaMemcpyDeviceToDevice, Caffe::stream()));
+        CUDA_CHECK(cudaMemcpyAsync(packed_.bias + cp, bias->gpu_data(), sizeof(float) * num_output_,
+                                   cudaMemcpyDeviceToDevice, Caffe::stream()));
+      }
+      packed_.b_version = bver;
+    }
+    packed_.cout_pad = 2 * cp;
+    const size_t bytes = (size_t)N * H * (W / 2) * 64 * 2;
+    patches_.reserve(bytes, split);
+    MSCNN_CHECK(mscnn_im2col3x3_c3_pair_to_planes(bottom[0]->gpu_data(), patches_.hi,
+                                                  split ? patches_.lo : nullptr, N, H, W, Caffe::stream()));
+    typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
+    d.x_hi = patches_.hi;
+    d.x_lo = split ? patches_.lo : nullptr;
+    d.N = N; d.H = H; d.W = W / 2; d.C = 64;
+    d.w_hi = packed_.w.hi;
+    d.w_lo = split ? packed_.w.lo : nullptr;
+    d.bias = packed_.bias;
+    d.Cout = 2 * cp; d.Cout_pad = 2 * cp;
+    d.KH = d.KW = 1;
+    d.relu = fuse_relu_ ? 1 : 0;
+    d.out_mode = MSCNN_OUT_NHWC_BF16;
+    d.y_hi = y.hi;
+    d.y_lo = y.lo;
+    MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
+    return;
+  }
+  if (first_path && !(conv1_mode && std::string(conv1_mode) == "patch")) {
     typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
     MSCNN_CHECK(mscnn_conv3x3_c3_forward(bottom[0]->gpu_data(), this->blobs_[0]->gpu_data(),
                                          bias ? bias->gpu_data() : nullptr, y.hi, y.lo, N, H, W, num_output_,
                                          y.cpad, fuse_relu_ ? 1 : 0, Caffe::stream()));
     return;
   }
-  // (MSCNN_CONV1_GEMM=1: the same layer as a 1x1 GEMM over 27-tap patch planes, kept for comparison)
+  // (MSCNN_CONV1=patch: the same layer as a 1x1 GEMM over single-pixel 27-tap patch planes, kept for comparison)
   const bool patch_path = first_path;
   if (patch_path) {
     ensure_packed_conv(&packed_, this->blobs_[0].get(), bias, split, num_output_, 27, 1, 1, 64);

@@ -119,6 +119,76 @@ __global__ void im2col3x3_c3_kernel(const float* __restrict__ x, __nv_bfloat16* 
   }
 }
 
+// conv1_1 as a tensor-core GEMM with K = 64 fully used: one GEMM row = TWO horizontally adjacent
+// pixels.  Channels [0,27) hold the 27 taps (c*9 + dy*3 + dx) of pixel 2j, [27,54) those of pixel
+// 2j+1, [54,64) zero.  With block-diagonal weights [2*Cout][64] the 1x1 GEMM emits
+// [pixel 2j: Cout ch][pixel 2j+1: Cout ch] per row, which in memory IS the NHWC tensor [N][H][W][Cout].
+// One thread per pixel pair; one 128-byte row per plane.
+__global__ void im2col3x3_c3_pair_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int N, int H, int W) {
+  const int W2 = W / 2;
+  const size_t total = (size_t)N * H * W2;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int j = idx % W2;
+  const int h = (idx / W2) % H;
+  const int n = idx / ((size_t)W2 * H);
+  __align__(16) __nv_bfloat16 vh[64];
+  __align__(16) __nv_bfloat16 vl[64];
+#pragma unroll
+  for (int k = 54; k < 64; ++k) {
+    vh[k] = __float2bfloat16_rn(0.f);
+    vl[k] = vh[k];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const int hh = h + dy - 1;
+      float col[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ww = 2 * j + q - 1;
+        col[q] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((size_t)(n * 3 + c) * H + hh) * W + ww] : 0.f;
+      }
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        split_bf16(col[dx], vh[c * 9 + dy * 3 + dx], vl[c * 9 + dy * 3 + dx]);
+        split_bf16(col[dx + 1], vh[27 + c * 9 + dy * 3 + dx], vl[27 + c * 9 + dy * 3 + dx]);
+      }
+    }
+  }
+  uint4* oh = reinterpret_cast<uint4*>(hi + idx * 64);
+  const uint4* sh = reinterpret_cast<const uint4*>(vh);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) oh[q] = sh[q];
+  if (lo) {
+    uint4* ol = reinterpret_cast<uint4*>(lo + idx * 64);
+    const uint4* sl = reinterpret_cast<const uint4*>(vl);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) ol[q] = sl[q];
+  }
+}
+
+// block-diagonal weights for the pixel-pair GEMM: out[r][k], r < 2*Cout_pad, k < 64
+//   r <  Cout_pad: out[r][k]      = w[r][k]              for k < 27
+//   r >= Cout_pad: out[r][27 + k] = w[r - Cout_pad][k]   for k < 27
+__global__ void pack_conv1_pair_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int Cout, int Cout_pad) {
+  const int total = 2 * Cout_pad * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % 64, r = i / 64;
+    const int half = r / Cout_pad, co = r % Cout_pad;
+    const int t = k - 27 * half;
+    float v = 0.f;
+    if (co < Cout && t >= 0 && t < 27) v = w[co * 27 + t];
+    __nv_bfloat16 h, l;
+    split_bf16(v, h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
 // out[(co*KH*KW + tap)*Cin_pad + ci] = w[((co*Cin + ci)*KH*KW) + tap]
 __global__ void pack_conv_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
                                    __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int taps,
@@ -157,19 +227,20 @@ __global__ void pack_fc_w_kernel(const float* __restrict__ w, __nv_bfloat16* __r
   }
 }
 
-// out[(tap*Cout + co)][ci] = w[co][ci][tap]  (rows beyond taps*Cout and channels beyond Cin are zero)
+// out[n = dx*Cout + co][dy][ci] = w[co][ci][dy][dx]  (rows beyond k*Cout and channels beyond Cin are zero)
 __global__ void pack_head_w_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ hi,
-                                   __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int taps, int N_pad,
+                                   __nv_bfloat16* __restrict__ lo, int Cout, int Cin, int k, int N_pad,
                                    int Cin_pad) {
-  const size_t total = (size_t)N_pad * Cin_pad;
+  const size_t total = (size_t)N_pad * k * Cin_pad;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const int ci = i % Cin_pad;
-    const int n = i / Cin_pad;
+    const int dy = (i / Cin_pad) % k;
+    const int n = i / ((size_t)Cin_pad * k);
     float v = 0.f;
-    if (n < taps * Cout && ci < Cin) {
-      const int tap = n / Cout, co = n - tap * Cout;
-      v = w[((size_t)co * Cin + ci) * taps + tap];
+    if (n < k * Cout && ci < Cin) {
+      const int dx = n / Cout, co = n - dx * Cout;
+      v = w[(((size_t)co * Cin + ci) * k + dy) * k + dx];
     }
     __nv_bfloat16 h, l;
     split_bf16(v, h, l);
@@ -178,7 +249,8 @@ __global__ void pack_head_w_kernel(const float* __restrict__ w, __nv_bfloat16* _
   }
 }
 
-// One thread per output pixel; taps in (dy, dx) order like the reference's im2col column order.
+// y[n][co][h][w] = bias[co] + sum_dx P[(n, h, w + dx - pad)][dx*COUT + co]; one thread per output pixel,
+// a warp covers 32 consecutive w so every P row is touched by k neighbouring lanes.
 template <int COUT>
 __global__ void head_gather_kernel(const float* __restrict__ P, int ld, const float* __restrict__ bias,
                                    float* __restrict__ y, int N, int H, int W, int k, int pad) {
@@ -186,25 +258,21 @@ __global__ void head_gather_kernel(const float* __restrict__ P, int ld, const fl
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int w = idx % W;
-  const int h = (idx / W) % H;
-  const int n = idx / ((size_t)W * H);
+  const size_t row0 = idx - w;  // pixel index of (n, h, 0)
   float acc[COUT];
 #pragma unroll
   for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
-  for (int dy = 0; dy < k; ++dy) {
-    const int hh = h + dy - pad;
-    if (hh < 0 || hh >= H) continue;
-    for (int dx = 0; dx < k; ++dx) {
-      const int ww = w + dx - pad;
-      if (ww < 0 || ww >= W) continue;
-      const float* src = P + ((size_t)(n * H + hh) * W + ww) * ld + (dy * k + dx) * COUT;
+  for (int dx = 0; dx < k; ++dx) {
+    const int ww = w + dx - pad;
+    if (ww < 0 || ww >= W) continue;
+    const float* src = P + (row0 + ww) * ld + dx * COUT;
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] = acc[c] + src[c];
-    }
+    for (int c = 0; c < COUT; ++c) acc[c] = acc[c] + src[c];
   }
   const size_t plane = (size_t)H * W;
+  const size_t n = idx / plane, hw = idx - n * plane;
 #pragma unroll
-  for (int c = 0; c < COUT; ++c) y[((size_t)n * COUT + c) * plane + (size_t)h * W + w] = acc[c] + bias[c];
+  for (int c = 0; c < COUT; ++c) y[(n * COUT + c) * plane + hw] = acc[c] + bias[c];
 }
 
 static int check_launch(const char* what) {
@@ -278,18 +346,18 @@ extern "C" int mscnn_pack_fc_weights(const float* w, void* hi, void* lo, int Nou
 
 extern "C" int mscnn_pack_head_weights(const float* w, void* hi, void* lo, int Cout, int Cin, int k, int N_pad,
                                        int Cin_pad, void* stream) {
-  if (!w || !hi || Cout <= 0 || Cin <= 0 || k <= 0 || N_pad < k * k * Cout || Cin_pad < Cin || Cin_pad % 64)
+  if (!w || !hi || Cout <= 0 || Cin <= 0 || k <= 0 || N_pad < k * Cout || Cin_pad < Cin || Cin_pad % 64)
     return MSCNN_ERR_INVALID;
-  const size_t total = (size_t)N_pad * Cin_pad;
+  const size_t total = (size_t)N_pad * k * Cin_pad;
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
   pack_head_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout,
-                                                              Cin, k * k, N_pad, Cin_pad);
+                                                              Cin, k, N_pad, Cin_pad);
   return check_launch("pack_head_w");
 }
 
 extern "C" int mscnn_head_gather(const float* P, int ld, const float* bias, float* y, int N, int H, int W,
                                  int Cout, int k, int pad, void* stream) {
-  if (!P || !bias || !y || N <= 0 || H <= 0 || W <= 0 || k <= 0 || ld < k * k * Cout) return MSCNN_ERR_INVALID;
+  if (!P || !bias || !y || N <= 0 || H <= 0 || W <= 0 || k <= 0 || ld < k * Cout) return MSCNN_ERR_INVALID;
   const size_t total = (size_t)N * H * W;
   const unsigned blocks = (unsigned)((total + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
@@ -299,4 +367,22 @@ extern "C" int mscnn_head_gather(const float* P, int ld, const float* bias, floa
     default: return MSCNN_ERR_INVALID;  // the MS-CNN heads have cls_num + 4 = 6 or 9 channels
   }
   return check_launch("head_gather");
+}
+
+extern "C" int mscnn_im2col3x3_c3_pair_to_planes(const float* x, void* hi, void* lo, int N, int H, int W,
+                                                 void* stream) {
+  if (!x || !hi || N <= 0 || H <= 0 || W <= 0 || (W & 1)) return MSCNN_ERR_INVALID;
+  const size_t total = (size_t)N * H * (W / 2);
+  const int threads = 128;
+  im2col3x3_c3_pair_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, H, W);
+  return check_launch("im2col3x3_c3_pair");
+}
+
+extern "C" int mscnn_pack_conv1_pair_weights(const float* w, void* hi, void* lo, int Cout, int Cout_pad,
+                                             void* stream) {
+  if (!w || !hi || Cout <= 0 || Cout_pad < Cout || Cout_pad % 32) return MSCNN_ERR_INVALID;
+  pack_conv1_pair_w_kernel<<<(2 * Cout_pad * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout, Cout_pad);
+  return check_launch("pack_conv1_pair_w");
 }
