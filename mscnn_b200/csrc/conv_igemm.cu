@@ -487,8 +487,10 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
 
   // shared memory plan
   const int b_bytes = BN * kBlockK * 2;
-  // fat stages (all four operand tiles): opt-in, see profiles/r01_ncu_conv_summary.md
-  p.fat = (split && BN <= 128 && getenv("MSCNN_FAT")) ? 1 : 0;
+  // fat stages (A_hi, A_lo, B_hi, B_lo of a k-block in one stage, three MMAs per K step) for the
+  // narrow-N layers of the fp32-faithful path: A_hi / B_hi are fetched once instead of twice and a
+  // barrier round trip covers 3x the MMAs (conv1_2: 6.3 -> 3.9 ms, profiles/r01_probe_layers*.log).
+  p.fat = (split && BN <= 128 && !getenv("MSCNN_NO_FAT")) ? 1 : 0;
   // M sub-tiles per CTA tile: for narrow N one weight tile should feed several activation tiles
   // (fewer hot-line weight fetches and barrier round trips per MMA).  2 * mt * BN TMEM columns <= 512.
   const int m_tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;

@@ -50,12 +50,12 @@ def main():
                 for fat in ((False, True) if split else (False,)):
                     os.environ["MSCNN_MT"] = mt
                     if fat:
-                        os.environ["MSCNN_FAT"] = "1"
+                        os.environ.pop("MSCNN_NO_FAT", None)
                     else:
-                        os.environ.pop("MSCNN_FAT", None)
+                        os.environ["MSCNN_NO_FAT"] = "1"
                     t = timeit(lambda: ops.conv_forward(xp, wp, 1, relu=True))
                     msg += f"  mt{mt}{'+fat' if fat else ''} {t:.3f}"
-            os.environ.pop("MSCNN_FAT", None)
+            os.environ.pop("MSCNN_NO_FAT", None)
             os.environ.pop("MSCNN_MT", None)
             t = timeit(lambda: ops.conv_forward(xp, wp, 1, relu=True))
             msg += f"  default {t:.3f} ms"
