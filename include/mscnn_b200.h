@@ -88,6 +88,11 @@ typedef struct mscnn_conv_desc {
   void* y_hi;
   void* y_lo; /* may be NULL even when x_lo is set (bf16-only output) */
   float* y_f32;
+  /* Optional fused PoolingLayer (MAX, 2x2, stride 2; pooling_layer.cu:158-190) on the NHWC_BF16
+   * output: pool planes [N][Ho/2][Wo/2][Cout_pad] (Ho, Wo even).  With pool_hi set, y_hi may be
+   * NULL: the un-pooled tensor is then never written to HBM. */
+  void* pool_hi;
+  void* pool_lo;
 } mscnn_conv_desc;
 MSCNN_API int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream);
 

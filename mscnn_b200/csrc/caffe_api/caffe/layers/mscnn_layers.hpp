@@ -42,6 +42,8 @@ class InputLayer : public Layer<Dtype> {
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {}
 };
 
+template <typename Dtype> class PoolingLayer;
+
 /// ConvolutionLayer: conv_layer.cpp:8-40 / base_conv_layer.cpp:15-254 (stride 1, group 1, dilation 1:
 /// every Convolution in the shipped deploy nets).  blobs_[0] = [Cout, Cin, kh, kw], blobs_[1] = [Cout].
 template <typename Dtype>
@@ -56,8 +58,18 @@ class ConvolutionLayer : public Layer<Dtype> {
   // mscnn_b200 extension: fold the in-place ReLU that follows into the epilogue (set by Net).
   void set_fuse_relu(bool f) { fuse_relu_ = f; }
   bool fuse_relu() const { return fuse_relu_; }
+  // mscnn_b200 extension (set by Net): the 2x2/2 MAX PoolingLayer that follows is computed in this
+  // layer's epilogue and written to `pool_top`; with keep_full == false nothing else reads this
+  // layer's own top, which is then never written (its blob holds no data).
+  void set_fused_pool(PoolingLayer<Dtype>* pool, Blob<Dtype>* pool_top, bool keep_full) {
+    fused_pool_ = pool; fused_pool_top_ = pool_top; fused_keep_full_ = keep_full;
+  }
+  int num_output() const { return num_output_; }
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  PoolingLayer<Dtype>* fused_pool_ = nullptr;
+  Blob<Dtype>* fused_pool_top_ = nullptr;
+  bool fused_keep_full_ = true;
   int num_output_, channels_, kernel_h_, kernel_w_, pad_h_, pad_w_;
   bool bias_term_, fuse_relu_;
   PackedParam packed_;
@@ -114,9 +126,14 @@ class PoolingLayer : public Layer<Dtype> {
   virtual inline int ExactNumBottomBlobs() const { return 1; }
   virtual inline int MinTopBlobs() const { return 1; }
   virtual inline int MaxTopBlobs() const { return 1; }
+  int kernel() const { return kernel_; }
+  int stride() const { return stride_; }
+  int mode() const { return mode_; }
+  void mark_done_by_producer() { done_by_producer_ = true; }  // the convolution's epilogue pooled already
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
   int kernel_, stride_, mode_, pooled_h_, pooled_w_;
+  bool done_by_producer_ = false;
 };
 
 /// SplitLayer: split_layer.cpp:9-31 (forward = share data).

@@ -77,6 +77,7 @@ class Net {
   int AppendBottom(const NetParameter& param, const int layer_id, const int bottom_id,
                    set<string>* available_blobs, map<string, int>* blob_name_to_idx);
   void FuseLayers();
+  void FusePooling();
 
   string name_;
   Phase phase_;

@@ -294,10 +294,21 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
   d.Cout_pad = packed_.cout_pad;
   d.relu = fuse_relu_ ? 1 : 0;
   if (packed_.cout_pad % 64 == 0) {
-    typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
     d.out_mode = MSCNN_OUT_NHWC_BF16;
-    d.y_hi = y.hi;
-    d.y_lo = y.lo;
+    const int ho = top[0]->height(), wo = top[0]->width();
+    const bool pool_here = fused_pool_ && !patch_path && (ho % 2 == 0) && (wo % 2 == 0);
+    if (!pool_here || fused_keep_full_) {
+      typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
+      d.y_hi = y.hi;
+      d.y_lo = y.lo;
+    }
+    if (pool_here) {
+      fused_pool_top_->Reshape(top[0]->num(), num_output_, ho / 2, wo / 2);
+      typename Blob<Dtype>::Planes q = fused_pool_top_->mutable_planes(split);
+      d.pool_hi = q.hi;
+      d.pool_lo = q.lo;
+      fused_pool_->mark_done_by_producer();
+    }
   } else {
     d.out_mode = MSCNN_OUT_NCHW_F32;  // narrow heads (LFCN_*): straight into the Caffe layout
     d.y_f32 = top[0]->mutable_gpu_data();
@@ -383,6 +394,10 @@ void PoolingLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, const vect
 }
 template <typename Dtype>
 void PoolingLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  if (done_by_producer_) {  // computed in the producing convolution's epilogue
+    done_by_producer_ = false;
+    return;
+  }
   const bool split = Caffe::split();
   typename Blob<Dtype>::Planes x = bottom[0]->planes(split);
   typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);

@@ -136,7 +136,10 @@ void Net<Dtype>::Init(const NetParameter& in_param) {
   for (size_t i = 0; i < blob_names_.size(); ++i) blob_names_index_[blob_names_[i]] = (int)i;
   for (size_t i = 0; i < layer_names_.size(); ++i) layer_names_index_[layer_names_[i]] = (int)i;
   layer_ms_.assign(layers_.size(), 0.f);
-  if (!std::getenv("MSCNN_NO_FUSION")) FuseLayers();
+  if (!std::getenv("MSCNN_NO_FUSION")) {
+    FuseLayers();
+    if (!std::getenv("MSCNN_NO_POOL_FUSION")) FusePooling();
+  }
 }
 
 template <typename Dtype>
@@ -242,6 +245,50 @@ void Net<Dtype>::FuseLayers() {
     // only the FIRST producer in execution order leads; it needs every sibling's inputs
     if (!sibs.empty()) sibs[0].layer->set_siblings(sibs);
     cat->set_fused(true);
+  }
+}
+
+// (c) a 2x2 / stride-2 MAX Pooling whose bottom was written by a Convolution (possibly through its
+// fused in-place ReLU) is computed in that convolution's epilogue.  If nothing else reads the
+// un-pooled blob it is not written at all.
+template <typename Dtype>
+void Net<Dtype>::FusePooling() {
+  const int L = (int)layers_.size();
+  for (int i = 0; i < L; ++i) {
+    PoolingLayer<Dtype>* pool = dynamic_cast<PoolingLayer<Dtype>*>(layers_[i].get());
+    if (!pool || pool->kernel() != 2 || pool->stride() != 2 || pool->mode() != MSCNN_POOL_MAX) continue;
+    const int blob_id = bottom_id_vecs_[i][0];
+    // walk back over the writers of the blob: [conv] or [conv, fused in-place relu]
+    int conv_idx = -1;
+    bool ok = true;
+    for (int k = i - 1; k >= 0 && conv_idx < 0 && ok; --k) {
+      bool writes = false;
+      for (size_t t = 0; t < top_id_vecs_[k].size(); ++t) writes = writes || (top_id_vecs_[k][t] == blob_id);
+      if (!writes) continue;
+      if (ReLULayer<Dtype>* r = dynamic_cast<ReLULayer<Dtype>*>(layers_[k].get())) {
+        if (!r->fused()) ok = false;
+        continue;
+      }
+      if (dynamic_cast<ConvolutionLayer<Dtype>*>(layers_[k].get())) conv_idx = k;
+      else ok = false;
+    }
+    if (!ok || conv_idx < 0) continue;
+    ConvolutionLayer<Dtype>* conv = static_cast<ConvolutionLayer<Dtype>*>(layers_[conv_idx].get());
+    if (conv->num_output() % 64 != 0) continue;
+    // other readers of the un-pooled blob (in-place layers excluded)?
+    int readers = 0;
+    for (int k = 0; k < L; ++k) {
+      if (k == i) continue;
+      for (size_t b = 0; b < bottom_id_vecs_[k].size(); ++b) {
+        if (bottom_id_vecs_[k][b] != blob_id) continue;
+        const bool in_place = b < top_id_vecs_[k].size() && top_id_vecs_[k][b] == blob_id;
+        if (!in_place) ++readers;
+      }
+    }
+    bool is_net_output = false;
+    for (size_t o = 0; o < net_output_blob_indices_.size(); ++o)
+      is_net_output = is_net_output || (net_output_blob_indices_[o] == blob_id);
+    conv->set_fused_pool(pool, top_vecs_[i][0], readers > 0 || is_net_output);
   }
 }
 

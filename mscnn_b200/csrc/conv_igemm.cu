@@ -45,6 +45,8 @@ struct IgemmParams {
   int relu;
   int out_mode;    // MSCNN_OUT_NHWC_BF16, MSCNN_OUT_NCHW_F32 or MSCNN_OUT_NHWC_F32
   int has_lo_out;
+  int pool;           // fused 2x2 / stride-2 MAX pooling of the output tile (box_w, box_h even)
+  int store_full;     // also store the un-pooled tile (0 when only the pooling layer reads it)
   int stages, epi_bufs;
   int fat;            // split mode with all four operand tiles (A_hi, A_lo, B_hi, B_lo) in one stage
   int mt;             // M sub-tiles (128 pixels each) per CTA tile: one weight tile feeds mt activation tiles
@@ -70,7 +72,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   const __grid_constant__ CUtensorMap tmB_hi,
                   const __grid_constant__ CUtensorMap tmB_lo,
                   const __grid_constant__ CUtensorMap tmO_hi,
-                  const __grid_constant__ CUtensorMap tmO_lo, const IgemmParams p) {
+                  const __grid_constant__ CUtensorMap tmO_lo,
+                  const __grid_constant__ CUtensorMap tmP_hi,
+                  const __grid_constant__ CUtensorMap tmP_lo, const IgemmParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM, BLOCK_N);
 
@@ -86,7 +90,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   const uint32_t sA = smem_base;
   const uint32_t sB = sA + S * a_stride;
   const uint32_t sEpi = sB + S * b_stride;  // 1024-aligned: kABytes, kBBytes are multiples of 1024
-  const int epi_buf_bytes = kABytes * (p.has_lo_out ? 2 : 1);
+  constexpr int kPoolBytes = kABytes / 4;  // pooled tile: 32 rows x 128 B
+  const int epi_buf_bytes = (kABytes + (p.pool ? kPoolBytes : 0)) * (p.has_lo_out ? 2 : 1);
   const uint32_t sMisc = sEpi + p.epi_bufs * epi_buf_bytes;
   uint8_t* misc_gen = smem_gen + (sMisc - smem_base);
   float* bias_s = reinterpret_cast<float*>(misc_gen);  // BLOCK_N floats
@@ -113,6 +118,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     if (p.out_mode == MSCNN_OUT_NHWC_BF16) {
       ptx::prefetch_tmap(&tmO_hi);
       if (p.has_lo_out) ptx::prefetch_tmap(&tmO_lo);
+      if (p.pool) {
+        ptx::prefetch_tmap(&tmP_hi);
+        if (p.has_lo_out) ptx::prefetch_tmap(&tmP_lo);
+      }
     }
     for (int s = 0; s < S; ++s) {
       ptx::mbar_init(full_bar(s), 1);
@@ -320,14 +329,74 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                                "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3])
                                : "memory");
               }
+              const uint32_t pbuf = buf + kABytes * (p.has_lo_out ? 2 : 1);  // pooled staging [hi][lo]
+              if (p.pool) {
+                // Fused PoolingLayer (MAX, 2x2, stride 2; pooling_layer.cpp:128-187) on the staged tile:
+                // exactly what pool_kernel would compute from the stored planes (value = hi + lo).
+                ptx::named_bar_sync(kEpiBarId, kEpiThreads);
+                const int pw_box = p.box_w >> 1, phw_box = pw_box * (p.box_h >> 1);
+                const int prows = phw_box * p.box_n;  // <= 32
+                for (int item = et; item < prows * 8; item += kEpiThreads) {
+                  const int pr = item >> 3, j = item & 7;
+                  const int dn = pr / phw_box, rem = pr - dn * phw_box;
+                  const int ph = rem / pw_box, pwi = rem - ph * pw_box;
+                  const int r00 = dn * hw_box + (2 * ph) * p.box_w + 2 * pwi;
+                  float best[8];
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) best[e] = -3.402823466e+38f;
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) {
+                    const int r = r00 + (c >> 1) * p.box_w + (c & 1);
+                    const uint32_t a = buf + r * 128 + static_cast<uint32_t>((j ^ (r & 7)) << 4);
+                    uint32_t xh[4], xl[4] = {0u, 0u, 0u, 0u};
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(xh[0]), "=r"(xh[1]), "=r"(xh[2]), "=r"(xh[3]) : "r"(a));
+                    if (p.has_lo_out)
+                      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                   : "=r"(xl[0]), "=r"(xl[1]), "=r"(xl[2]), "=r"(xl[3]) : "r"(a + kABytes));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                      const float v0 = __uint_as_float(xh[q] << 16) + __uint_as_float(xl[q] << 16);
+                      const float v1 = __uint_as_float(xh[q] & 0xFFFF0000u) + __uint_as_float(xl[q] & 0xFFFF0000u);
+                      best[2 * q] = (v0 > best[2 * q]) ? v0 : best[2 * q];
+                      best[2 * q + 1] = (v1 > best[2 * q + 1]) ? v1 : best[2 * q + 1];
+                    }
+                  }
+                  uint32_t oh[4], ol[4];
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(best[2 * q]), h1 = __float2bfloat16_rn(best[2 * q + 1]);
+                    oh[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                            (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(best[2 * q] - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(best[2 * q + 1] - __bfloat162float(h1));
+                    ol[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+                            (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+                  }
+                  const uint32_t pa = pbuf + pr * 128 + static_cast<uint32_t>((j ^ (pr & 7)) << 4);
+                  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa), "r"(oh[0]), "r"(oh[1]),
+                               "r"(oh[2]), "r"(oh[3]) : "memory");
+                  if (p.has_lo_out)
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa + kPoolBytes), "r"(ol[0]),
+                                 "r"(ol[1]), "r"(ol[2]), "r"(ol[3]) : "memory");
+                }
+              }
               ptx::fence_proxy_async_smem();
               ptx::named_bar_sync(kEpiBarId, kEpiThreads);
               if (issuer) {
                 const int c0 = n_base + chunk * 64;
-                ptx::tma_store_4d(&tmO_hi, buf, c0, tw * p.box_w, th * p.box_h, tn * p.box_n);
-                if (p.has_lo_out)
-                  ptx::tma_store_4d(&tmO_lo, buf + kABytes, c0, tw * p.box_w, th * p.box_h,
-                                    tn * p.box_n);
+                if (!p.pool || p.store_full) {
+                  ptx::tma_store_4d(&tmO_hi, buf, c0, tw * p.box_w, th * p.box_h, tn * p.box_n);
+                  if (p.has_lo_out)
+                    ptx::tma_store_4d(&tmO_lo, buf + kABytes, c0, tw * p.box_w, th * p.box_h,
+                                      tn * p.box_n);
+                }
+                if (p.pool) {
+                  ptx::tma_store_4d(&tmP_hi, pbuf, c0, tw * (p.box_w >> 1), th * (p.box_h >> 1), tn * p.box_n);
+                  if (p.has_lo_out)
+                    ptx::tma_store_4d(&tmP_lo, pbuf + kPoolBytes, c0, tw * (p.box_w >> 1), th * (p.box_h >> 1),
+                                      tn * p.box_n);
+                }
                 ptx::tma_store_commit();
               }
               if (++ebuf == p.epi_bufs) ebuf = 0;
@@ -407,11 +476,12 @@ static int pick_block_n(int cout_pad) {
 }
 
 // Choose the pixel box (bw, bh, bn), bw*bh*bn <= 128, that wastes the fewest MMA rows.
-static void pick_box(int N, int Ho, int Wo, int* bw_o, int* bh_o, int* bn_o) {
+static void pick_box(int N, int Ho, int Wo, bool even, int* bw_o, int* bh_o, int* bn_o) {
   double best = -1.0;
   int b_w = 1, b_h = 1, b_n = 1;
   for (int bw = 1; bw <= 128 && bw <= Wo; ++bw) {
     for (int bh = 1; bh * bw <= 128 && bh <= Ho; ++bh) {
+      if (even && ((bw & 1) || (bh & 1))) continue;  // 2x2 pooling windows must not straddle tiles
       int bn = 128 / (bw * bh);
       if (bn > N) bn = N;
       // rows of a K-major SW128 tile come in groups of 8: any row count works for TMA, the
@@ -434,12 +504,12 @@ static void pick_box(int N, int Ho, int Wo, int* bw_o, int* bh_o, int* bn_o) {
 }
 
 template <int BLOCK_N>
-static cudaError_t launch_igemm(const CUtensorMap maps[6], const IgemmParams& p, int grid,
+static cudaError_t launch_igemm(const CUtensorMap maps[8], const IgemmParams& p, int grid,
                                 size_t smem, cudaStream_t stream) {
   auto kern = conv_igemm_kernel<BLOCK_N>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);
+  kern<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
   return cudaGetLastError();
 }
 
@@ -458,7 +528,9 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (Ho <= 0 || Wo <= 0 || d->N <= 0) return MSCNN_ERR_INVALID;
   const int BN = pick_block_n(d->Cout_pad);
   if (d->Cout_pad % BN != 0 || d->Cout > d->Cout_pad) return MSCNN_ERR_INVALID;
-  if (d->out_mode == MSCNN_OUT_NHWC_BF16 && (BN < 64 || !d->y_hi)) return MSCNN_ERR_INVALID;
+  const bool pool = (d->out_mode == MSCNN_OUT_NHWC_BF16 && d->pool_hi != nullptr);
+  if (d->out_mode == MSCNN_OUT_NHWC_BF16 && (BN < 64 || (!d->y_hi && !pool))) return MSCNN_ERR_INVALID;
+  if (pool && ((Ho & 1) || (Wo & 1))) return MSCNN_ERR_INVALID;  // fused pooling: even output extents only
   if ((d->out_mode == MSCNN_OUT_NCHW_F32 || d->out_mode == MSCNN_OUT_NHWC_F32) && !d->y_f32) return MSCNN_ERR_INVALID;
 
   IgemmParams p;
@@ -469,14 +541,18 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   p.pad_h = d->pad_h;
   p.pad_w = d->pad_w;
   p.cin_chunks = d->C / 64;
-  pick_box(d->N, Ho, Wo, &p.box_w, &p.box_h, &p.box_n);
+  pick_box(d->N, Ho, Wo, pool, &p.box_w, &p.box_h, &p.box_n);
   p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
   p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
   p.tiles_n = (d->N + p.box_n - 1) / p.box_n;
   p.n_tiles = d->Cout_pad / BN;
   p.relu = d->relu;
   p.out_mode = d->out_mode;
-  p.has_lo_out = (d->out_mode == MSCNN_OUT_NHWC_BF16 && d->y_lo != nullptr) ? 1 : 0;
+  p.has_lo_out = (d->out_mode == MSCNN_OUT_NHWC_BF16 && (d->y_lo != nullptr || (pool && d->pool_lo != nullptr))) ? 1 : 0;
+  p.pool = pool ? 1 : 0;
+  p.store_full = (d->y_hi != nullptr) ? 1 : 0;
+  if (pool && p.store_full && p.has_lo_out && !d->y_lo) return MSCNN_ERR_INVALID;
+  if (pool && p.has_lo_out && !d->pool_lo) return MSCNN_ERR_INVALID;
   p.bias = d->bias;
   p.out_f32 = d->y_f32;
   p.out_n = d->N;
@@ -501,7 +577,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (mt > kMaxMt) mt = kMaxMt;
   if (mt < 1) mt = 1;
   while (mt > 1 && (2 * mt * BN > 512 || m_tiles_total % mt != 0 || m_tiles_total / mt * p.n_tiles < mscnn_sm_count())) mt >>= 1;
-  const int epi_unit = (d->out_mode == MSCNN_OUT_NHWC_BF16) ? kABytes * (p.has_lo_out ? 2 : 1) : 0;
+  const int epi_unit = (d->out_mode == MSCNN_OUT_NHWC_BF16) ? (kABytes + (pool ? kABytes / 4 : 0)) * (p.has_lo_out ? 2 : 1) : 0;
   const int misc = BN * 4 + 8 * (2 * 8 + 4) + 16 + 1024 /*alignment slack*/;
   const int budget = 227 * 1024;
   int epi_bufs = (epi_unit == 0) ? 0 : 2;
@@ -530,7 +606,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
             d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.num_terms, stages,
             epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
-  CUtensorMap maps[6];
+  CUtensorMap maps[8];
   memset(maps, 0, sizeof(maps));
   const uint32_t abox[4] = {64u, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
   const uint64_t adim[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
@@ -553,9 +629,13 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   }
   if (d->out_mode == MSCNN_OUT_NHWC_BF16) {
     const uint64_t odim[4] = {(uint64_t)d->Cout_pad, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->N};
-    rc = tmap_nhwc_bf16(&maps[4], d->y_hi, odim, abox);
-    if (rc) return rc;
-    if (p.has_lo_out) {
+    if (d->y_hi) {
+      rc = tmap_nhwc_bf16(&maps[4], d->y_hi, odim, abox);
+      if (rc) return rc;
+    } else {
+      maps[4] = maps[0];
+    }
+    if (p.has_lo_out && d->y_lo) {
       rc = tmap_nhwc_bf16(&maps[5], d->y_lo, odim, abox);
       if (rc) return rc;
     } else {
@@ -564,6 +644,20 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   } else {
     maps[4] = maps[0];
     maps[5] = maps[0];
+  }
+  maps[6] = maps[4];
+  maps[7] = maps[5];
+  if (p.pool) {
+    const uint64_t pdim[4] = {(uint64_t)d->Cout_pad, (uint64_t)(Wo / 2), (uint64_t)(Ho / 2), (uint64_t)d->N};
+    const uint32_t pbox[4] = {64u, (uint32_t)(p.box_w / 2), (uint32_t)(p.box_h / 2), (uint32_t)p.box_n};
+    rc = tmap_nhwc_bf16(&maps[6], d->pool_hi, pdim, pbox);
+    if (rc) return rc;
+    if (p.has_lo_out) {
+      rc = tmap_nhwc_bf16(&maps[7], d->pool_lo, pdim, pbox);
+      if (rc) return rc;
+    } else {
+      maps[7] = maps[6];
+    }
   }
 
   const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n / p.mt * p.n_tiles;

@@ -114,7 +114,7 @@ def pack_fc_weights(w: torch.Tensor, b: torch.Tensor | None, split: bool, c: int
 
 
 def conv_forward(x: Planes, w: PackedWeights, pad: int, relu: bool, out_f32: bool = False,
-                 out_split: bool | None = None):
+                 out_split: bool | None = None, pool: str | None = None):
     """Convolution (stride 1) + bias (+ReLU).  Returns Planes, or an NCHW fp32 tensor when
     ``out_f32``.  An InnerProduct is the KH=KW=H=W=1 case."""
     n, h, wd, c = x.hi.shape
@@ -138,6 +138,16 @@ def conv_forward(x: Planes, w: PackedWeights, pad: int, relu: bool, out_f32: boo
         y_lo = torch.empty_like(y_hi) if out_split else None
         d.out_mode, d.y_hi, d.y_lo = capi.OUT_NHWC_BF16, capi.ptr(y_hi), capi.ptr(y_lo)
         out = Planes(y_hi, y_lo, w.cout)
+        if pool:   # "both": conv output and its fused 2x2 max pool; "only": pooled tensor alone
+            p_hi = torch.empty((n, ho // 2, wo // 2, cout_pad), dtype=torch.bfloat16, device=x.hi.device)
+            p_lo = torch.empty_like(p_hi) if out_split else None
+            d.pool_hi, d.pool_lo = capi.ptr(p_hi), capi.ptr(p_lo)
+            pooled = Planes(p_hi, p_lo, w.cout)
+            if pool == "only":
+                d.y_hi, d.y_lo = None, None
+                out = pooled
+            else:
+                out = (out, pooled)
     capi.check(capi.lib().mscnn_conv_forward(d, _stream()), "conv_forward")
     return out
 

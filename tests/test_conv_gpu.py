@@ -182,6 +182,31 @@ def test_conv1_1_direct(cuda, split):
         _report("conv1_1_direct", got, ref, 2.0 ** -8, 1e-5 * rms)
 
 
+@pytest.mark.parametrize("split", [True, False], ids=["split", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 192, 64), (1, 64, 128, 320, 128), (2, 128, 24, 80, 256), (3, 64, 10, 12, 64)])
+def test_conv_fused_pool(cuda, split, shape):
+    """mscnn_conv_forward with pool_hi set == conv followed by mscnn_pool_forward, bit for bit; the
+    pool-only form (no un-pooled store) gives the same pooled planes."""
+    from mscnn_b200 import ops
+    n, cin, h, w, cout = shape
+    g = torch.Generator(device="cpu").manual_seed(21)
+    x = torch.randn((n, cin, h, w), generator=g).to(cuda)
+    wt = (torch.randn((cout, cin, 3, 3), generator=g) * (2.0 / (cin * 9)) ** 0.5).to(cuda)
+    b = (torch.randn((cout,), generator=g) * 0.1).to(cuda)
+    xp = ops.nchw_to_planes(x, split)
+    wp = ops.pack_conv_weights(wt, b, split)
+    y_ref = ops.conv_forward(xp, wp, 1, relu=True)
+    p_ref = ops.pool_forward(y_ref, 2, 2)
+    y_both, p_both = ops.conv_forward(xp, wp, 1, relu=True, pool="both")
+    p_only = ops.conv_forward(xp, wp, 1, relu=True, pool="only")
+    torch.cuda.synchronize()
+    assert torch.equal(y_both.hi, y_ref.hi)
+    for cand in (p_both, p_only):
+        assert torch.equal(cand.hi, p_ref.hi)
+        if split:
+            assert torch.equal(cand.lo, p_ref.lo)
+
+
 def test_layout_roundtrip(cuda):
     from mscnn_b200 import ops
     g = torch.Generator(device="cpu").manual_seed(5)

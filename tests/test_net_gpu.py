@@ -21,10 +21,18 @@ GOLD = Path(__file__).resolve().parent / "golden"
 SUB = 7919
 
 
-def _build(proto, n, h, w, precision="fp32"):
+def _build(proto, n, h, w, precision="fp32", pool_fusion=True):
+    """pool_fusion=False keeps the un-pooled conv1_2 / conv2_2 / conv3_3 blobs materialised (with the
+    fusion on they are never written: only the pooling layers read them)."""
+    import os
     from mscnn_b200 import net as mnet, synth
     mnet.set_precision(precision)
-    net = mnet.Net(proto)
+    if not pool_fusion:
+        os.environ["MSCNN_NO_POOL_FUSION"] = "1"
+    try:
+        net = mnet.Net(proto)
+    finally:
+        os.environ.pop("MSCNN_NO_POOL_FUSION", None)
     net.set_params(synth.make_weights(net.layers()))
     net.set_input("data", synth.make_images(n, h, w))
     return net
@@ -54,7 +62,7 @@ def _match_rows(got, ref, tol):
 def test_e2e_kitti_7s_vs_reference(cuda, precision, feat_tol, row_tol, min_match):
     from mscnn_b200 import models
     g = np.load(GOLD / "e2e_7s_192x640.npz")
-    net = _build(models.kitti(192, 640, 7, False, batch=2), 2, 192, 640, precision)
+    net = _build(models.kitti(192, 640, 7, False, batch=2), 2, 192, 640, precision, pool_fusion=False)
     out = net.forward()
     # ---- trunk features (subsampled) --------------------------------------------------------
     worst = {}
@@ -91,6 +99,20 @@ def test_e2e_kitti_7s_vs_reference(cuda, precision, feat_tol, row_tol, min_match
             # head itself is checked element-by-element in test_head_stage_isolated_vs_reference.
             assert _rel_ok(a, r, 1e-3, m2).mean() >= 0.99, name
     print(f"[{precision}] worst trunk rel err {worst}; proposals {len(got_ps)} vs {len(ref_ps)}, matched {frac:.4f}")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pool_fusion_is_bit_identical(cuda, precision):
+    """Conv epilogue with fused 2x2 max pooling (pool1/2/3) vs the separate pooling kernel: the pooled
+    planes and therefore every downstream blob must be bit-identical."""
+    from mscnn_b200 import models
+    a = _build(models.kitti(192, 640, 8, False, batch=2), 2, 192, 640, precision, pool_fusion=True)
+    b = _build(models.kitti(192, 640, 8, False, batch=2), 2, 192, 640, precision, pool_fusion=False)
+    oa, ob = a.forward(), b.forward()
+    for blob in ["pool1", "pool2", "pool3", "conv4_3", "conv6_1"]:
+        assert np.array_equal(a.blob(blob), b.blob(blob)), blob
+    for k in oa:
+        assert np.array_equal(oa[k], ob[k]), k
 
 
 def test_head_taps_path_equals_direct_conv(cuda, monkeypatch):
