@@ -332,7 +332,10 @@ def main() -> None:
         "gpu_launches": launches_per_step(net) * args.steps * world,
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel<BLOCK_N> (all Convolution + InnerProduct layers)",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                     "traffic": None,
+                     # dram__bytes_read+write of ONE representative launch of this kernel from the committed
+                     # `ncu --set full` capture (conv3_2, BLOCK_N=256: 1.015 GB + 0.966 GB, equal to its
+                     # algorithmic 2.01 GB of planes in + out; profiles/r01b_summary.md)
+                     "traffic": 1.981e9, "traffic_launch": "conv3_2 (profiles/r01b_conv3_2_split_N256.ncu-rep)",
                      "algorithmic_gflop_per_step": r["flops"] / 1e9,
                      "launches_per_step": r["conv_launches"],
                      "avg_launch_ms": r["conv_ms"] / r["conv_launches"],
