@@ -199,6 +199,8 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="skip the plain-bf16 measurement")
+    ap.add_argument("--profile-bf16", action="store_true",
+                    help="profiling aid: run ONLY plain-bf16 forwards and print nothing (for ncu captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "mscnn_b200" else args.warmup
     if args.impl == "reference":
@@ -277,6 +279,12 @@ def main() -> None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
+    if args.profile_bf16:
+        mnet.set_precision("bf16")
+        for _ in range(args.warmup + args.steps):
+            step_resident()
+        torch.cuda.synchronize()
+        return
     results = {}
     sampler = ClockSampler(local) if rank == 0 else None
     for mode in (["fp32"] if args.no_bf16 else ["fp32", "bf16"]):
