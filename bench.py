@@ -34,9 +34,6 @@ sys.path.insert(0, str(ROOT))
 NET_H, NET_W, BATCH = 768, 2560, 8
 WORKLOAD = "mscnn-8s-768 KITTI-car forward, batch 8 per GPU, 3x768x2560 synthetic (BASELINE.json configs[2])"
 CPU_SAMPLE_H, CPU_SAMPLE_W = 192, 640          # 1/16 of the pixels of one 768x2560 image
-KERNELS_PER_LAYER = {"Convolution": 1, "InnerProduct": 1, "Pooling": 1, "Deconvolution": 1, "BoxOutput": 5,
-                     "ROIPooling": 1}
-DETECT_KERNELS = 4
 
 
 def peaks() -> dict:
@@ -112,12 +109,6 @@ def conv_flops(net, n_images: int) -> tuple[float, int]:
             total += 2.0 * net.blob_shape(name)[0] * no * k
             launches += 1
     return total, launches
-
-
-def launches_per_step(net) -> int:
-    n = sum(KERNELS_PER_LAYER.get(t, 0) for t in net.layer_types) + DETECT_KERNELS
-    n += 1  # conv1_1 patch gather
-    return n
 
 
 def run_reference(args) -> None:
@@ -210,7 +201,7 @@ def main() -> None:
     import numpy as np
     import torch
     import torch.distributed as dist
-    from mscnn_b200 import models, net as mnet, synth
+    from mscnn_b200 import capi, models, net as mnet, synth
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -267,17 +258,23 @@ def main() -> None:
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = capi.lib().mscnn_kernel_launch_count()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         torch.cuda.synchronize()
+        launched = capi.lib().mscnn_kernel_launch_count() - n0
         if world > 1:
             dist.barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        ms = torch.tensor([e0.elapsed_time(e1), float(launched)], device=dev)
         if world > 1:
+            both = ms.clone()
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+            dist.all_reduce(both, op=dist.ReduceOp.SUM)
+            ms[1] = both[1]
+        timed.launched = int(ms[1].item())     # kernels launched by libmscnn_b200 in the timed region, all ranks
+        return float(ms[0].item())
 
     if args.profile_bf16:
         mnet.set_precision("bf16")
@@ -292,6 +289,7 @@ def main() -> None:
         if mode == "fp32" and sampler:
             sampler.start()
         ms = timed(step_resident, args.steps, args.warmup)
+        launched = timed.launched
         clocks = sampler.stop() if (mode == "fp32" and sampler) else None
         props = torch.tensor([float(net.num_proposals())], device=dev)
         if world > 1:
@@ -306,7 +304,7 @@ def main() -> None:
         all_ms = sum(min(lt[k], lt2[k]) for k in lt)
         flops, conv_launches = conv_flops(net, B)
         results[mode] = dict(ms=ms, ms_e2e=ms_e2e, props=float(props.item()), conv_ms=conv_ms, all_ms=all_ms,
-                             flops=flops, conv_launches=conv_launches, clocks=clocks,
+                             flops=flops, conv_launches=conv_launches, clocks=clocks, launched=launched,
                              top=sorted(((min(lt[k], lt2[k]), k) for k in lt), reverse=True)[:6],
                              layers={k: round(min(lt[k], lt2[k]), 3) for k in lt if min(lt[k], lt2[k]) >= 0.02})
     mnet.set_precision("fp32")
@@ -337,7 +335,8 @@ def main() -> None:
                 "h2d_bytes_per_step": B * 3 * NET_H * NET_W * 4 * world,
                 "d2h_bytes_per_step": (B * cap * 5 * 4 + B * 4) * world,
                 "api": "mscnn_b200.net.Net.set_input(pinned host) / forward_only / detect + D2H of detections"},
-        "gpu_launches": launches_per_step(net) * args.steps * world,
+        # counted by the library itself (mscnn_kernel_launch_count) inside the timed resident region, all ranks
+        "gpu_launches": r["launched"],
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel<BLOCK_N> (all Convolution + InnerProduct layers)",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      # dram__bytes_read+write of ONE representative launch of this kernel from the committed

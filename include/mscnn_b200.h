@@ -61,6 +61,8 @@ extern "C" {
 /* library / device ------------------------------------------------------------------ */
 MSCNN_API const char* mscnn_version(void);
 MSCNN_API int mscnn_sm_count(void);
+/* Number of CUDA kernels this library has launched in this process so far (all entry points). */
+MSCNN_API unsigned long long mscnn_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * Convolution (stride 1) / InnerProduct with fused bias and optional ReLU.

@@ -22,6 +22,7 @@
 #include <stdio.h>
 
 #include "mscnn_b200.h"
+#include "launch_count.h"
 
 namespace mscnn {
 
@@ -583,21 +584,26 @@ extern "C" int mscnn_box_output_forward(const mscnn_box_output_cfg* cfg, int N, 
   int* keep_idx = (int*)(ws + w.keep_idx);
   int* keep_count = (int*)(ws + w.keep_count);
 
+  mscnn::note_launch();
   box_decode_kernel<<<dim3((A + 255) / 256, N), 256, 0, stream>>>(p, N, keys, boxes);
   const size_t topk_smem = (size_t)Kpad * 8;
   cudaError_t e = cudaFuncSetAttribute(box_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)topk_smem);
   if (e != cudaSuccess) return MSCNN_ERR_CUDA;
+  mscnn::note_launch();
   box_topk_kernel<<<N, kTopkThreads, topk_smem, stream>>>(keys, boxes, A, cfg->max_nms_num, Kpad, sboxes,
                                                          sscores, counts);
   const int words = Kpad / 64;
+  mscnn::note_launch();
   nms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words, cfg->iou_thr,
                                                            cfg->nms_type, mask);
   const size_t scan_smem = (size_t)64 * words * 8;
   e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
   if (e != cudaSuccess) return MSCNN_ERR_CUDA;
+  mscnn::note_launch();
   nms_scan_kernel<<<N, kScanThreads, scan_smem, stream>>>(mask, counts, Kpad, words, cfg->max_post_nms_num,
                                                           keep_idx, keep_count);
+  mscnn::note_launch();
   box_finalize_kernel<<<1, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, N, Kpad, proposals,
                                              proposals_score, num_out);
   e = cudaGetLastError();
@@ -677,15 +683,19 @@ extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, cons
   cudaError_t e = cudaFuncSetAttribute(detect_decode_sort_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return MSCNN_ERR_CUDA;
+  mscnn::note_launch();
   detect_decode_sort_kernel<<<N, kTopkThreads, smem, stream>>>(p, proposals_score, cls_pred, bbox_pred,
                                                               num_rois, Kpad, dboxes, sboxes, sscores, counts);
   const int words = Kpad / 64;
+  mscnn::note_launch();
   bbnms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words,
                                                              (double)cfg->nms_overlap, mask);
   const size_t scan_smem = (size_t)64 * words * 8;
   e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
   if (e != cudaSuccess) return MSCNN_ERR_CUDA;
+  mscnn::note_launch();
   nms_scan_kernel<<<N, kScanThreads, scan_smem, stream>>>(mask, counts, Kpad, words, 0, keep_idx, keep_count);
+  mscnn::note_launch();
   detect_write_kernel<<<N, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, Kpad,
                                             cfg->max_rois_per_image, dets, det_counts);
   e = cudaGetLastError();

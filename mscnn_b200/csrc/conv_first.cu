@@ -13,6 +13,7 @@
 #include <stdio.h>
 
 #include "mscnn_b200.h"
+#include "launch_count.h"
 
 namespace mscnn {
 
@@ -114,6 +115,7 @@ extern "C" int mscnn_conv3x3_c3_forward(const float* x, const float* w, const fl
         return MSCNN_ERR_CUDA;
       }
     }
+    mscnn::note_launch();
     mscnn::conv3x3_c3_kernel<<<grid, mscnn::kFirstTile, 0, st>>>(x, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, N,
                                                                  H, W, Cout_pad, cg, relu);
   }

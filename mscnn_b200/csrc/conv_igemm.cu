@@ -33,6 +33,7 @@
 #include "mscnn_b200.h"
 #include "ptx_sm100.cuh"
 #include "tmap.h"
+#include "launch_count.h"
 
 namespace mscnn {
 
@@ -509,6 +510,7 @@ static cudaError_t launch_igemm(const CUtensorMap maps[8], const IgemmParams& p,
   auto kern = conv_igemm_kernel<BLOCK_N>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
+  mscnn::note_launch();
   kern<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
   return cudaGetLastError();
 }

@@ -6,6 +6,7 @@
 #include <stdio.h>
 
 #include "mscnn_b200.h"
+#include "launch_count.h"
 
 namespace mscnn {
 
@@ -296,6 +297,7 @@ extern "C" int mscnn_nchw_f32_to_planes(const float* x, void* hi, void* lo, int 
     return MSCNN_ERR_INVALID;
   if ((long)N * (Cpad / 64) > 65535 || H > 65535) return MSCNN_ERR_INVALID;
   dim3 grid((W + 31) / 32, H, N * (Cpad / 64));
+  mscnn::note_launch();
   nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, C, H, W, Cpad);
   return check_launch("nchw_to_planes");
@@ -307,6 +309,7 @@ extern "C" int mscnn_planes_to_nchw_f32(const void* hi, const void* lo, float* y
     return MSCNN_ERR_INVALID;
   if ((long)N * (Cpad / 64) > 65535 || H > 65535) return MSCNN_ERR_INVALID;
   dim3 grid((W + 31) / 32, H, N * (Cpad / 64));
+  mscnn::note_launch();
   planes_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, y, N, C, H, W, Cpad);
   return check_launch("planes_to_nchw");
@@ -317,6 +320,7 @@ extern "C" int mscnn_im2col3x3_c3_to_planes(const float* x, void* hi, void* lo, 
   if (!x || !hi || N <= 0 || H <= 0 || W <= 0) return MSCNN_ERR_INVALID;
   const size_t total = (size_t)N * H * W;
   const int threads = 128;
+  mscnn::note_launch();
   im2col3x3_c3_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0,
                         (cudaStream_t)stream>>>(x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, H, W);
   return check_launch("im2col3x3_c3");
@@ -328,6 +332,7 @@ extern "C" int mscnn_pack_conv_weights(const float* w, void* hi, void* lo, int C
     return MSCNN_ERR_INVALID;
   const size_t total = (size_t)Cout_pad * KH * KW * Cin_pad;
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  mscnn::note_launch();
   pack_conv_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout, Cin, KH * KW, Cout_pad, Cin_pad);
   return check_launch("pack_conv_w");
@@ -339,6 +344,7 @@ extern "C" int mscnn_pack_fc_weights(const float* w, void* hi, void* lo, int Nou
     return MSCNN_ERR_INVALID;
   const size_t total = (size_t)Nout_pad * H * W * Cpad;
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  mscnn::note_launch();
   pack_fc_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
       w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Nout, C, H * W, Nout_pad, Cpad);
   return check_launch("pack_fc_w");
@@ -350,6 +356,7 @@ extern "C" int mscnn_pack_head_weights(const float* w, void* hi, void* lo, int C
     return MSCNN_ERR_INVALID;
   const size_t total = (size_t)N_pad * k * Cin_pad;
   const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  mscnn::note_launch();
   pack_head_w_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout,
                                                               Cin, k, N_pad, Cin_pad);
   return check_launch("pack_head_w");
@@ -362,8 +369,8 @@ extern "C" int mscnn_head_gather(const float* P, int ld, const float* bias, floa
   const unsigned blocks = (unsigned)((total + 127) / 128);
   cudaStream_t st = (cudaStream_t)stream;
   switch (Cout) {
-    case 6: head_gather_kernel<6><<<blocks, 128, 0, st>>>(P, ld, bias, y, N, H, W, k, pad); break;
-    case 9: head_gather_kernel<9><<<blocks, 128, 0, st>>>(P, ld, bias, y, N, H, W, k, pad); break;
+    case 6: mscnn::note_launch(); head_gather_kernel<6><<<blocks, 128, 0, st>>>(P, ld, bias, y, N, H, W, k, pad); break;
+    case 9: mscnn::note_launch(); head_gather_kernel<9><<<blocks, 128, 0, st>>>(P, ld, bias, y, N, H, W, k, pad); break;
     default: return MSCNN_ERR_INVALID;  // the MS-CNN heads have cls_num + 4 = 6 or 9 channels
   }
   return check_launch("head_gather");
@@ -374,6 +381,7 @@ extern "C" int mscnn_im2col3x3_c3_pair_to_planes(const float* x, void* hi, void*
   if (!x || !hi || N <= 0 || H <= 0 || W <= 0 || (W & 1)) return MSCNN_ERR_INVALID;
   const size_t total = (size_t)N * H * (W / 2);
   const int threads = 128;
+  mscnn::note_launch();
   im2col3x3_c3_pair_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
       x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, H, W);
   return check_launch("im2col3x3_c3_pair");
@@ -382,6 +390,7 @@ extern "C" int mscnn_im2col3x3_c3_pair_to_planes(const float* x, void* hi, void*
 extern "C" int mscnn_pack_conv1_pair_weights(const float* w, void* hi, void* lo, int Cout, int Cout_pad,
                                              void* stream) {
   if (!w || !hi || Cout <= 0 || Cout_pad < Cout || Cout_pad % 32) return MSCNN_ERR_INVALID;
+  mscnn::note_launch();
   pack_conv1_pair_w_kernel<<<(2 * Cout_pad * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       w, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, Cout, Cout_pad);
   return check_launch("pack_conv1_pair_w");

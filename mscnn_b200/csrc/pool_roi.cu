@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include "mscnn_b200.h"
+#include "launch_count.h"
 
 namespace mscnn {
 
@@ -275,6 +276,7 @@ extern "C" int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi
   const int Ho = (H - kernel + stride - 1) / stride + 1;
   const int Wo = (W - kernel + stride - 1) / stride + 1;
   const size_t total = (size_t)N * Ho * Wo * (C / 8);
+  mscnn::note_launch();
   pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, N,
       H, W, C, Ho, Wo, kernel, stride, mode);
@@ -298,6 +300,7 @@ extern "C" int mscnn_roi_pool_multi_forward(const void* x_hi, const void* x_lo, 
   }
   if (R == 0) return MSCNN_OK;
   const size_t total = (size_t)R * pooled_h * pooled_w * 32;  // one warp per (ROI, bin)
+  mscnn::note_launch();
   roi_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, rois, R, N, H, W, C, pooled_h, pooled_w,
       spatial_scale, var, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total);
@@ -317,6 +320,7 @@ extern "C" int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const 
   if (!x_hi || !y_hi || !w || N <= 0 || H <= 0 || W <= 0 || C % 8 || Creal > C) return MSCNN_ERR_INVALID;
   if ((x_lo == nullptr) != (y_lo == nullptr)) return MSCNN_ERR_INVALID;
   const size_t total = (size_t)N * 2 * H * 2 * W * (C / 8);
+  mscnn::note_launch();
   deconv2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, w, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo,
       N, H, W, C, Creal);
@@ -326,6 +330,7 @@ extern "C" int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const 
 extern "C" int mscnn_relu_planes(void* hi, void* lo, size_t count, void* stream) {
   if (!hi || count % 8) return MSCNN_ERR_INVALID;
   if (count == 0) return MSCNN_OK;
+  mscnn::note_launch();
   relu_planes_kernel<<<grid_for(count / 8, 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)hi,
                                                                                  (__nv_bfloat16*)lo, count / 8);
   return launch_check("relu_planes");
@@ -334,6 +339,7 @@ extern "C" int mscnn_relu_planes(void* hi, void* lo, size_t count, void* stream)
 extern "C" int mscnn_relu_f32(float* x, size_t count, void* stream) {
   if (!x) return MSCNN_ERR_INVALID;
   if (count == 0) return MSCNN_OK;
+  mscnn::note_launch();
   relu_f32_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(x, count);
   return launch_check("relu_f32");
 }
@@ -342,6 +348,7 @@ extern "C" int mscnn_concat_planes(const void* x, void* y, size_t pixels, int C,
                                    void* stream) {
   if (!x || !y || C % 8 || Ctot % 8 || offset % 8 || offset + C > Ctot) return MSCNN_ERR_INVALID;
   if (pixels == 0) return MSCNN_OK;
+  mscnn::note_launch();
   concat_planes_kernel<<<grid_for(pixels * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x, (__nv_bfloat16*)y, pixels, C, Ctot, offset);
   return launch_check("concat_planes");

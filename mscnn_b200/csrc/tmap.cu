@@ -1,4 +1,5 @@
 #include "tmap.h"
+#include "launch_count.h"
 
 #include <cudaTypedefs.h>
 #include <stdio.h>
@@ -68,7 +69,13 @@ int tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t row
   return MSCNN_OK;
 }
 
+std::atomic<unsigned long long> g_kernel_launches{0};
+
 }  // namespace mscnn
+
+extern "C" unsigned long long mscnn_kernel_launch_count(void) {
+  return mscnn::g_kernel_launches.load(std::memory_order_relaxed);
+}
 
 extern "C" int mscnn_sm_count(void) {
   static int cached = 0;
