@@ -223,6 +223,37 @@ MSCNN_API int mscnn_roi_pool_multi_forward(const void* x_hi, const void* x_lo, i
                                  void* y_hi, void* y_lo, int out_channels_total, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * ROIAlign (cascade WIDER-face nets): bilinear samples on the (pooled_h+1) x (pooled_w+1) grid of bin
+ * corners of each (pad_ratio-extended) ROI.  Replaces ROIAlignLayer::Forward_gpu
+ * (src/caffe/layers/roi_align_layer.cu:21-98; CPU semantics roi_align_layer.cpp:49-139).
+ *   x planes [N][H][W][C]; rois fp32 [R][5];
+ *   y planes [R][pooled_h+1][pooled_w+1][out_channels_total], channels [offset, offset + C). */
+MSCNN_API int mscnn_roi_align_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                            const float* rois, int R, int pooled_h, int pooled_w, float spatial_scale,
+                            float pad_ratio, void* y_hi, void* y_lo, int out_channels_total,
+                            int out_channel_offset, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Per-ROI layers of the cascade deploy nets, all on NCHW fp32 device arrays.
+ * DecodeBBox: replaces DecodeBBoxLayer::Forward_cpu (src/caffe/layers/decode_bbox_layer.cpp:53-124, CPU
+ *   only in the reference) + DecodeBBoxesWithPrior (src/caffe/util/math_functions.cpp:46-77), TEST
+ *   phase: out[i] = [img, x1, y1, x2, y2] = prior[i] moved by the class-1 deltas bbox_pred[i][4..8).
+ *   mean4 / std4 may be NULL (0 / 1, decode_bbox_layer.cpp:33-35).
+ * Softmax: replaces SoftmaxLayer::Forward_cpu (softmax_layer.cpp:28-62) over `channels` with
+ *   `outer` x `inner` independent positions.
+ * Eltwise: replaces EltwiseLayer::Forward_cpu (eltwise_layer.cpp:46-96); `bottoms` is a HOST array
+ *   of 2..MSCNN_MAX_ELTWISE device pointers, coeffs (host, SUM only) may be NULL (all 1). */
+#define MSCNN_MAX_ELTWISE 8
+#define MSCNN_ELTWISE_PROD 0
+#define MSCNN_ELTWISE_SUM 1
+#define MSCNN_ELTWISE_MAX 2
+MSCNN_API int mscnn_decode_bbox_forward(const float* bbox_pred, const float* prior, int R, int bbox_dim,
+                              const float* mean4, const float* std4, float* out, void* stream);
+MSCNN_API int mscnn_softmax_forward(const float* x, int outer, int channels, int inner, float* y, void* stream);
+MSCNN_API int mscnn_eltwise_forward(const float* const* bottoms, int num_bottoms, int op, const float* coeffs,
+                          size_t count, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Final detections for one class: softmax probability, bbox-delta decode, clip, greedy NMS.
  * Replaces the MATLAB code after net.forward in the reference driver
  * (examples/kitti_car/run_mscnn_detection.m:75-120, utils/bbNms.m:112-126).
@@ -244,6 +275,17 @@ MSCNN_API int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const
                              const float* cls_pred, const float* bbox_pred, const int* num_rois,
                              void* workspace, size_t workspace_bytes, float* dets, int* det_counts,
                              void* stream);
+
+/* Cascade variant: replaces the MATLAB code after net.forward in examples/kitti_car/run_cascademscnn.m:99-126
+ * (+ utils/bbNms.m:112-126).  The net already holds decoded boxes and probabilities:
+ *   proposals [R][5] (the stage's ROIs: rows whose width or height is 0 are dropped), cls_prob [R][num_cls]
+ *   (Softmax output), output_bbox [R][5] (DecodeBBox output).  Boxes are rescaled by ratio_*, clipped to
+ *   [0, org_*], converted to [x y w h] with w = x2 - x1 + 1, and NMS'ed; cfg->bbox_mean/std and
+ *   proposal_thr are unused.  Same workspace size and outputs as mscnn_detect_postprocess. */
+MSCNN_API int mscnn_cascade_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals,
+                                     const float* cls_prob, const float* output_bbox, const int* num_rois,
+                                     void* workspace, size_t workspace_bytes, float* dets, int* det_counts,
+                                     void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Net facade: caffe::Net<float> of the Caffe-API mirror (mscnn_b200/csrc/caffe_api) for hosts that
@@ -285,6 +327,11 @@ MSCNN_API int mscnn_net_set_layer_timing(void* net, int on);
 MSCNN_API int mscnn_net_layer_times(void* net, float* ms);                 /* ms per layer, last forward */
 MSCNN_API int mscnn_net_num_proposals(void* net, int image);               /* image < 0: whole batch */
 MSCNN_API int mscnn_net_detect(void* net, const mscnn_detect_cfg* cfg, float* dets_dev, int* det_counts_dev);
+/* cascade nets: the caller names the stage's blobs like run_cascademscnn.m:36-48 does
+ * (e.g. "proposals_3rd", "cls_prob_3rd", "output_bbox_3rd"). */
+MSCNN_API int mscnn_net_detect_cascade(void* net, const mscnn_detect_cfg* cfg, const char* proposals_blob,
+                             const char* cls_prob_blob, const char* output_bbox_blob, float* dets_dev,
+                             int* det_counts_dev);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "libmscnn_b200.so"
 
 OK = 0
+ELTWISE_PROD, ELTWISE_SUM, ELTWISE_MAX = 0, 1, 2
 ERR_INVALID = -1
 ERR_CUDA = -2
 ERR_NOMEM = -3
@@ -117,6 +118,17 @@ def _declare(L: C.CDLL) -> None:
     L.mscnn_roi_pool_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                          c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_int,
                                          c_void_p]
+    L.mscnn_roi_align_forward.restype = c_int
+    L.mscnn_roi_align_forward.argtypes = L.mscnn_roi_pool_forward.argtypes
+    L.mscnn_decode_bbox_forward.restype = c_int
+    L.mscnn_decode_bbox_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.mscnn_softmax_forward.restype = c_int
+    L.mscnn_softmax_forward.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]
+    L.mscnn_eltwise_forward.restype = c_int
+    L.mscnn_eltwise_forward.argtypes = [C.POINTER(c_void_p), c_int, c_int, c_void_p, C.c_size_t, c_void_p, c_void_p]
+    L.mscnn_cascade_detect_postprocess.restype = c_int
+    L.mscnn_cascade_detect_postprocess.argtypes = [C.POINTER(DetectCfg), c_int] + [c_void_p] * 5 + [C.c_size_t] + \
+        [c_void_p] * 3
     L.mscnn_detect_workspace_bytes.restype = c_int
     L.mscnn_detect_workspace_bytes.argtypes = [C.POINTER(DetectCfg), c_int, C.POINTER(C.c_size_t)]
     L.mscnn_detect_postprocess.restype = c_int

@@ -357,10 +357,17 @@ struct DetectParams {
 
 // One CTA per image: decode every ROI of the image, rank by probability (MATLAB sort 'descend'
 // is stable: ties keep the lower row first), leave boxes sorted in `sboxes` / `sscores`.
+// CASCADE = false: MS-CNN driver (run_mscnn_detection.m:75-116): prop = proposals_score [R][6],
+//   cls = cls_pred logits [R][num_cls], bbox = bbox_pred deltas [R][4 num_cls].
+// CASCADE = true: cascade driver (examples/kitti_car/run_cascademscnn.m:99-126): prop = the stage's
+//   proposals [R][5], cls = its Softmax output [R][num_cls], bbox = its DecodeBBox output [R][5]
+//   (already in net-input pixels); boxes are rescaled, clipped, converted to [x y w h] with the
+//   MATLAB "+1" width convention and nothing is thresholded (det_thr = -1).
+template <bool CASCADE>
 __global__ void __launch_bounds__(kTopkThreads)
-detect_decode_sort_kernel(const DetectParams p, const float* __restrict__ prop /*[R][6]*/,
-                          const float* __restrict__ cls /*[R][num_cls]*/,
-                          const float* __restrict__ bbox /*[R][4 num_cls]*/,
+detect_decode_sort_kernel(const DetectParams p, const float* __restrict__ prop,
+                          const float* __restrict__ cls,
+                          const float* __restrict__ bbox,
                           const int* __restrict__ num_rois, int Kpad, float4* __restrict__ dboxes,
                           float4* __restrict__ sboxes, float* __restrict__ sscores,
                           int* __restrict__ counts) {
@@ -376,6 +383,22 @@ detect_decode_sort_kernel(const DetectParams p, const float* __restrict__ prop /
   __syncthreads();
   const int id = p.cls_id - 1;
   for (int i = tid; i < cnt; i += kTopkThreads) {
+    if (CASCADE) {
+      const float* q = prop + (size_t)(start + i) * 5;
+      const float qw = q[3] - q[1] + 1.f, qh = q[4] - q[2] + 1.f;  // run_cascademscnn.m:113-117
+      if (qw == 0.f || qh == 0.f) continue;
+      const float* b = bbox + (size_t)(start + i) * 5;
+      float x1 = b[1] / p.ratio_w, y1 = b[2] / p.ratio_h, x2 = b[3] / p.ratio_w, y2 = b[4] / p.ratio_h;  // :101-102
+      x1 = fmaxf(0.f, x1); y1 = fmaxf(0.f, y1);                                                            // :104
+      x2 = fminf(x2, p.org_w); y2 = fminf(y2, p.org_h);                                                    // :105
+      const float w = x2 - x1 + 1.f, h = y2 - y1 + 1.f;                                                    // :106
+      const float prob = cls[(size_t)(start + i) * p.num_cls + id];
+      if (prob != prob) continue;  // bbNms: kp = bbs(:,5) > -inf drops NaN
+      dboxes[(size_t)n * Kpad + i] = make_float4(x1, y1, w, h);
+      sk[i] = ((unsigned long long)float_orderable(prob) << 32) | (unsigned int)(0xFFFFFFFFu - (unsigned)i);
+      atomicAdd(&s_valid, 1);
+      continue;
+    }
     const float* q = prop + (size_t)(start + i) * 6;
     const float px = q[1], py = q[2], pw = q[3] - q[1], ph = q[4] - q[2], psc = q[5];
     if (!(psc >= p.proposal_thr && pw != 0.f && ph != 0.f)) continue;
@@ -652,10 +675,9 @@ extern "C" int mscnn_detect_workspace_bytes(const mscnn_detect_cfg* cfg, int N, 
   return MSCNN_OK;
 }
 
-extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
-                                        const float* cls_pred, const float* bbox_pred, const int* num_rois,
-                                        void* workspace, size_t workspace_bytes, float* dets,
-                                        int* det_counts, void* stream_v) {
+static int detect_run(bool cascade, const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
+                      const float* cls_pred, const float* bbox_pred, const int* num_rois, void* workspace,
+                      size_t workspace_bytes, float* dets, int* det_counts, void* stream_v) {
   cudaStream_t stream = (cudaStream_t)stream_v;
   int Kpad;
   const int rc = det_cfg_check(cfg, N, &Kpad);
@@ -680,12 +702,19 @@ extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, cons
   int* keep_idx = (int*)(ws + w.keep_idx);
   int* keep_count = (int*)(ws + w.keep_count);
   const size_t smem = (size_t)Kpad * 8;
-  cudaError_t e = cudaFuncSetAttribute(detect_decode_sort_kernel,
+  cudaError_t e = cudaFuncSetAttribute(detect_decode_sort_kernel<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(detect_decode_sort_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem);
   if (e != cudaSuccess) return MSCNN_ERR_CUDA;
   mscnn::note_launch();
-  detect_decode_sort_kernel<<<N, kTopkThreads, smem, stream>>>(p, proposals_score, cls_pred, bbox_pred,
-                                                              num_rois, Kpad, dboxes, sboxes, sscores, counts);
+  if (cascade)
+    detect_decode_sort_kernel<true><<<N, kTopkThreads, smem, stream>>>(p, proposals_score, cls_pred, bbox_pred,
+                                                                      num_rois, Kpad, dboxes, sboxes, sscores, counts);
+  else
+    detect_decode_sort_kernel<false><<<N, kTopkThreads, smem, stream>>>(p, proposals_score, cls_pred, bbox_pred,
+                                                                       num_rois, Kpad, dboxes, sboxes, sscores, counts);
   const int words = Kpad / 64;
   mscnn::note_launch();
   bbnms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words,
@@ -704,4 +733,20 @@ extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, cons
     return MSCNN_ERR_CUDA;
   }
   return MSCNN_OK;
+}
+
+extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
+                                        const float* cls_pred, const float* bbox_pred, const int* num_rois,
+                                        void* workspace, size_t workspace_bytes, float* dets,
+                                        int* det_counts, void* stream) {
+  return detect_run(false, cfg, N, proposals_score, cls_pred, bbox_pred, num_rois, workspace, workspace_bytes,
+                    dets, det_counts, stream);
+}
+
+extern "C" int mscnn_cascade_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals,
+                                                const float* cls_prob, const float* output_bbox,
+                                                const int* num_rois, void* workspace, size_t workspace_bytes,
+                                                float* dets, int* det_counts, void* stream) {
+  return detect_run(true, cfg, N, proposals, cls_prob, output_bbox, num_rois, workspace, workspace_bytes, dets,
+                    det_counts, stream);
 }

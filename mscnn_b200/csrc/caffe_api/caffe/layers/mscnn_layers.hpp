@@ -1,4 +1,4 @@
-// The eleven layer types the MS-CNN deploy nets instantiate (census: SURVEY.md section 2), as
+// The layer types the MS-CNN and cascade deploy nets instantiate (census: SURVEY.md section 2 and 8(f)), as
 // caffe::Layer<Dtype> subclasses whose Forward_gpu calls the C ABI in include/mscnn_b200.h.
 // Class names, type() strings, blob layouts and parameter semantics are the reference's
 // (/root/reference/include/caffe/layers/*.hpp); the per-layer headers next to this file
@@ -272,6 +272,71 @@ class ROIPoolingLayer : public Layer<Dtype> {
   int concat_offset_, concat_channels_;
   vector<Sibling> siblings_;
   bool done_by_leader_ = false;
+};
+
+/// ROIAlignLayer: roi_align_layer.cpp:22-139 (cascade WIDER-face net).  top = [R, C, pooled_h+1, pooled_w+1].
+template <typename Dtype>
+class ROIAlignLayer : public Layer<Dtype> {
+ public:
+  explicit ROIAlignLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "ROIAlign"; }
+  virtual inline int MinBottomBlobs() const { return 2; }
+  virtual inline int MaxBottomBlobs() const { return 2; }
+  virtual inline int MinTopBlobs() const { return 1; }
+  virtual inline int MaxTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  int channels_, height_, width_, pooled_height_, pooled_width_, grid_height_, grid_width_;
+  float spatial_scale_, pad_ratio_;
+};
+
+/// DecodeBBoxLayer: decode_bbox_layer.cpp:17-124, TEST phase (2 bottoms: bbox_pred [R,8], prior ROIs [R,5]).
+/// CPU-only in the reference; here it stays on the device, so the cascade stages do not sync with the host.
+template <typename Dtype>
+class DecodeBBoxLayer : public Layer<Dtype> {
+ public:
+  explicit DecodeBBoxLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "DecodeBBox"; }
+  virtual inline int MinBottomBlobs() const { return 2; }
+  virtual inline int MaxBottomBlobs() const { return 3; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  float bbox_mean_[4], bbox_std_[4];
+};
+
+/// SoftmaxLayer: softmax_layer.cpp:10-62.
+template <typename Dtype>
+class SoftmaxLayer : public Layer<Dtype> {
+ public:
+  explicit SoftmaxLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "Softmax"; }
+  virtual inline int ExactNumBottomBlobs() const { return 1; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  int outer_num_, inner_num_, softmax_axis_;
+};
+
+/// EltwiseLayer: eltwise_layer.cpp:10-96 (PROD / SUM with coefficients / MAX).
+template <typename Dtype>
+class EltwiseLayer : public Layer<Dtype> {
+ public:
+  explicit EltwiseLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
+  virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  virtual inline const char* type() const { return "Eltwise"; }
+  virtual inline int MinBottomBlobs() const { return 2; }
+  virtual inline int ExactNumTopBlobs() const { return 1; }
+ protected:
+  virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
+  int op_;
+  vector<float> coeffs_;
 };
 
 }  // namespace caffe

@@ -717,6 +717,112 @@ void ROIPoolingLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, con
   }
 }
 
+// ------------------------------------------------------------------------------- ROIAlign
+template <typename Dtype>
+void ROIAlignLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  const ROIPoolingParameter& p = this->layer_param_.roi_pooling_param();  // roi_align_layer.cpp:22-37
+  CHECK_GT(p.pooled_h(), 0u) << "pooled_h must be > 0";
+  CHECK_GT(p.pooled_w(), 0u) << "pooled_w must be > 0";
+  pooled_height_ = p.pooled_h();
+  pooled_width_ = p.pooled_w();
+  grid_height_ = pooled_height_ + 1;
+  grid_width_ = pooled_width_ + 1;
+  spatial_scale_ = p.spatial_scale();
+  pad_ratio_ = p.pad_ratio();
+}
+template <typename Dtype>
+void ROIAlignLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  channels_ = bottom[0]->channels();
+  height_ = bottom[0]->height();
+  width_ = bottom[0]->width();
+  top[0]->Reshape(bottom[1]->num(), channels_, grid_height_, grid_width_);
+}
+template <typename Dtype>
+void ROIAlignLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  const bool split = Caffe::split();
+  typename Blob<Dtype>::Planes x = bottom[0]->planes(split);
+  typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
+  MSCNN_CHECK(mscnn_roi_align_forward(x.hi, x.lo, x.n, x.h, x.w, x.cpad, bottom[1]->gpu_data(), bottom[1]->num(),
+                                      pooled_height_, pooled_width_, spatial_scale_, pad_ratio_, y.hi, y.lo,
+                                      y.cpad, 0, Caffe::stream()));
+}
+
+// ----------------------------------------------------------------------------- DecodeBBox
+template <typename Dtype>
+void DecodeBBoxLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  const BBoxRegParameter& r = this->layer_param_.bbox_reg_param();  // decode_bbox_layer.cpp:20-36
+  if (r.bbox_mean_size() > 0 && r.bbox_std_size() > 0) {
+    CHECK_EQ(r.bbox_mean_size(), 4);
+    CHECK_EQ(r.bbox_std_size(), 4);
+    for (int i = 0; i < 4; ++i) {
+      bbox_mean_[i] = r.bbox_mean(i);
+      bbox_std_[i] = r.bbox_std(i);
+      CHECK_GT(bbox_std_[i], 0);
+    }
+  } else {
+    for (int i = 0; i < 4; ++i) { bbox_mean_[i] = 0.f; bbox_std_[i] = 1.f; }
+  }
+}
+template <typename Dtype>
+void DecodeBBoxLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  CHECK_EQ(bottom[0]->num(), bottom[1]->num());  // decode_bbox_layer.cpp:42-50
+  CHECK(bottom.size() < 3) << "mscnn_b200 is forward-only: DecodeBBox takes gt boxes only in the TRAIN phase";
+  CHECK_EQ(bottom[0]->channels(), 8);
+  CHECK_EQ(bottom[1]->channels(), 5);
+  top[0]->ReshapeLike(*bottom[1]);
+}
+template <typename Dtype>
+void DecodeBBoxLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  CHECK(this->phase_ == TEST) << "mscnn_b200 is forward-only: DecodeBBox runs in the TEST phase";
+  const int num = bottom[0]->num();
+  // TEST phase keeps every row (decode_bbox_layer.cpp:79-110), so the top has the priors' shape
+  top[0]->Reshape(num, bottom[1]->channels(), 1, 1);
+  MSCNN_CHECK(mscnn_decode_bbox_forward(bottom[0]->gpu_data(), bottom[1]->gpu_data(), num, bottom[0]->channels(),
+                                        bbox_mean_, bbox_std_, top[0]->mutable_gpu_data(), Caffe::stream()));
+}
+
+// -------------------------------------------------------------------------------- Softmax
+template <typename Dtype>
+void SoftmaxLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  softmax_axis_ = bottom[0]->CanonicalAxisIndex(this->layer_param_.softmax_param().axis());  // softmax_layer.cpp:10-25
+  top[0]->ReshapeLike(*bottom[0]);
+  outer_num_ = bottom[0]->count(0, softmax_axis_);
+  inner_num_ = bottom[0]->count(softmax_axis_ + 1);
+}
+template <typename Dtype>
+void SoftmaxLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  MSCNN_CHECK(mscnn_softmax_forward(bottom[0]->gpu_data(), outer_num_, bottom[0]->shape(softmax_axis_), inner_num_,
+                                    top[0]->mutable_gpu_data(), Caffe::stream()));
+}
+
+// -------------------------------------------------------------------------------- Eltwise
+template <typename Dtype>
+void EltwiseLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  const EltwiseParameter& p = this->layer_param_.eltwise_param();  // eltwise_layer.cpp:10-28
+  CHECK(p.coeff_size() == 0 || p.coeff_size() == (int)bottom.size())
+      << "Eltwise Layer takes one coefficient per bottom blob.";
+  CHECK(!(p.operation() == EltwiseParameter_EltwiseOp_PROD && p.coeff_size()))
+      << "Eltwise layer only takes coefficients for summation.";
+  CHECK_LE((int)bottom.size(), MSCNN_MAX_ELTWISE);
+  op_ = p.operation() == EltwiseParameter_EltwiseOp_PROD ? MSCNN_ELTWISE_PROD
+        : p.operation() == EltwiseParameter_EltwiseOp_MAX ? MSCNN_ELTWISE_MAX
+                                                          : MSCNN_ELTWISE_SUM;
+  coeffs_.assign(bottom.size(), 1.f);
+  for (int i = 0; i < p.coeff_size(); ++i) coeffs_[i] = p.coeff(i);
+}
+template <typename Dtype>
+void EltwiseLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  for (size_t i = 1; i < bottom.size(); ++i) CHECK(bottom[i]->shape() == bottom[0]->shape());
+  top[0]->ReshapeLike(*bottom[0]);
+}
+template <typename Dtype>
+void EltwiseLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
+  const float* in[MSCNN_MAX_ELTWISE];
+  for (size_t i = 0; i < bottom.size(); ++i) in[i] = bottom[i]->gpu_data();
+  MSCNN_CHECK(mscnn_eltwise_forward(in, (int)bottom.size(), op_, coeffs_.data(), (size_t)top[0]->count(),
+                                    top[0]->mutable_gpu_data(), Caffe::stream()));
+}
+
 INSTANTIATE_CLASS(InputLayer);
 INSTANTIATE_CLASS(ConvolutionLayer);
 INSTANTIATE_CLASS(DeconvolutionLayer);
@@ -728,6 +834,10 @@ INSTANTIATE_CLASS(InnerProductLayer);
 INSTANTIATE_CLASS(DropoutLayer);
 INSTANTIATE_CLASS(BoxOutputLayer);
 INSTANTIATE_CLASS(ROIPoolingLayer);
+INSTANTIATE_CLASS(ROIAlignLayer);
+INSTANTIATE_CLASS(DecodeBBoxLayer);
+INSTANTIATE_CLASS(SoftmaxLayer);
+INSTANTIATE_CLASS(EltwiseLayer);
 REGISTER_LAYER_CLASS(Input);
 REGISTER_LAYER_CLASS(Convolution);
 REGISTER_LAYER_CLASS(Deconvolution);
@@ -739,5 +849,9 @@ REGISTER_LAYER_CLASS(InnerProduct);
 REGISTER_LAYER_CLASS(Dropout);
 REGISTER_LAYER_CLASS(BoxOutput);
 REGISTER_LAYER_CLASS(ROIPooling);
+REGISTER_LAYER_CLASS(ROIAlign);
+REGISTER_LAYER_CLASS(DecodeBBox);
+REGISTER_LAYER_CLASS(Softmax);
+REGISTER_LAYER_CLASS(Eltwise);
 
 }  // namespace caffe

@@ -105,6 +105,7 @@ void Net<Dtype>::Init(const NetParameter& in_param) {
   name_ = param.name();
   map<string, int> blob_name_to_idx;
   set<string> available_blobs;
+  map<string, shared_ptr<Blob<Dtype> > > shared_params;
   const int L = param.layer_size();
   bottom_vecs_.resize(L);
   top_vecs_.resize(L);
@@ -127,6 +128,25 @@ void Net<Dtype>::Init(const NetParameter& in_param) {
       }
     }
     layers_[layer_id]->SetUp(bottom_vecs_[layer_id], top_vecs_[layer_id]);
+    // Net::AppendParam (net.cpp:448-538): layers whose ParamSpec carries the same non-empty name share
+    // one parameter blob (the cascade nets' third-stage ensemble heads, e.g. "roi_c1_w").  The reference
+    // makes the later blob ShareData() with the owner's; here the later layer simply holds the owner's
+    // Blob, so its version counter (used to re-pack weights lazily) is shared too.  Shapes must match
+    // (share_mode STRICT, the default, net.cpp:497-509).
+    vector<shared_ptr<Blob<Dtype> > >& layer_blobs = layers_[layer_id]->blobs();
+    for (int j = 0; j < (int)layer_blobs.size() && j < layer_param.param_size(); ++j) {
+      const string& pname = layer_param.param(j).name();
+      if (pname.empty()) continue;
+      typename map<string, shared_ptr<Blob<Dtype> > >::iterator owner = shared_params.find(pname);
+      if (owner == shared_params.end()) {
+        shared_params[pname] = layer_blobs[j];
+      } else {
+        CHECK(layer_blobs[j]->shape() == owner->second->shape())
+            << "Cannot share param '" << pname << "' with layer '" << layer_param.name()
+            << "': shape mismatch (" << owner->second->shape_string() << " vs " << layer_blobs[j]->shape_string() << ")";
+        layer_blobs[j] = owner->second;
+      }
+    }
   }
   // remaining available blobs are the outputs, in name order (std::set walk, net.cpp:268-274)
   for (set<string>::iterator it = available_blobs.begin(); it != available_blobs.end(); ++it) {

@@ -103,6 +103,13 @@ int mscnn_net_layer_param_string(void* h, int i, char* buf, int cap) {
   o << "|reg:";
   for (int k = 0; k < g.bbox_mean_size(); ++k) o << "m" << g.bbox_mean(k);
   for (int k = 0; k < g.bbox_std_size(); ++k) o << "s" << g.bbox_std(k);
+  o << "|softmax:" << p.softmax_param().axis();
+  const caffe::EltwiseParameter& e = p.eltwise_param();
+  o << "|elt:" << (int)e.operation();
+  for (int k = 0; k < e.coeff_size(); ++k) o << "," << e.coeff(k);
+  o << "|share:";
+  for (int k = 0; k < p.param_size(); ++k)
+    if (!p.param(k).name().empty()) o << k << "=" << p.param(k).name() << ",";
   const std::string s = o.str();
   if ((int)s.size() + 1 > cap) return MSCNN_ERR_INVALID;
   memcpy(buf, s.c_str(), s.size() + 1);
@@ -237,5 +244,28 @@ int mscnn_net_detect(void* hv, const mscnn_detect_cfg* cfg, float* dets_dev, int
                                   h->net->blob_by_name("cls_pred")->gpu_data(),
                                   h->net->blob_by_name("bbox_pred")->gpu_data(), h->box->num_out_device(),
                                   h->det_ws, h->det_ws_bytes, dets_dev, det_counts_dev, Caffe::stream());
+}
+int mscnn_net_detect_cascade(void* hv, const mscnn_detect_cfg* cfg, const char* proposals_blob,
+                             const char* cls_prob_blob, const char* output_bbox_blob, float* dets_dev,
+                             int* det_counts_dev) {
+  NetHandle* h = H(hv);
+  if (!h->box || !proposals_blob || !cls_prob_blob || !output_bbox_blob || !h->net->has_blob(proposals_blob) ||
+      !h->net->has_blob(cls_prob_blob) || !h->net->has_blob(output_bbox_blob))
+    return MSCNN_ERR_INVALID;
+  const int N = h->net->input_blobs()[0]->num();
+  size_t need = 0;
+  int rc = mscnn_detect_workspace_bytes(cfg, N, &need);
+  if (rc) return rc;
+  if (need > h->det_ws_bytes) {
+    if (h->det_ws) cudaFree(h->det_ws);
+    if (cudaMalloc(&h->det_ws, need) != cudaSuccess) return MSCNN_ERR_NOMEM;
+    h->det_ws_bytes = need;
+  }
+  if (h->net->blob_by_name(cls_prob_blob)->channels() != cfg->num_cls) return MSCNN_ERR_INVALID;
+  return mscnn_cascade_detect_postprocess(cfg, N, h->net->blob_by_name(proposals_blob)->gpu_data(),
+                                          h->net->blob_by_name(cls_prob_blob)->gpu_data(),
+                                          h->net->blob_by_name(output_bbox_blob)->gpu_data(),
+                                          h->box->num_out_device(), h->det_ws, h->det_ws_bytes, dets_dev,
+                                          det_counts_dev, Caffe::stream());
 }
 }

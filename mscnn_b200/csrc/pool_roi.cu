@@ -167,6 +167,71 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
   }
 }
 
+// ------------------------------------------------------------------------------ ROIAlign
+// ROIAlignLayer::Forward_cpu (src/caffe/layers/roi_align_layer.cpp:49-139; GPU twin
+// roi_align_layer.cu:21-98): bilinear samples on the (PH+1) x (PW+1) GRID of bin corners of the
+// (padded) ROI, in feature-map coordinates shifted by half a pixel.  Same work distribution as
+// roi_pool_kernel: one warp per (ROI, grid point), lanes over 8-channel groups, so the four
+// neighbour loads are coalesced 512-byte row segments.  fp32 arithmetic in the reference's order.
+__global__ void roi_align_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
+                                 const float* __restrict__ rois, int R, int N, int H, int W, int C, int PH,
+                                 int PW, float scale, float pad_ratio, __nv_bfloat16* __restrict__ yh,
+                                 __nv_bfloat16* __restrict__ yl, int Ctot, int c_off) {
+  const int cg = C / 8;
+  const int GH = PH + 1, GW = PW + 1;
+  const int lane = threadIdx.x & 31;
+  const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
+  const size_t points = (size_t)R * GH * GW;
+  for (size_t pt = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pt < points; pt += warps_total) {
+    const int pw = pt % GW;
+    const int ph = (pt / GW) % GH;
+    const int roi = pt / ((size_t)GW * GH);
+    const float* q = rois + (size_t)roi * 5;
+    int b = (int)q[0];
+    b = min(max(b, 0), N - 1);  // CHECKed by the reference (:63-64)
+    // :67-81
+    const float pad_w = (q[3] - q[1] + 1.f) * pad_ratio;
+    const float pad_h = (q[4] - q[2] + 1.f) * pad_ratio;
+    const float start_w = (q[1] - pad_w) * scale - 0.5f;
+    const float start_h = (q[2] - pad_h) * scale - 0.5f;
+    const float end_w = (q[3] + pad_w) * scale - 0.5f;
+    const float end_h = (q[4] + pad_h) * scale - 0.5f;
+    const float roi_h = end_h - start_h, roi_w = end_w - start_w;
+    const float bin_h = roi_h / (float)PH, bin_w = roi_w / (float)PW;
+    float hf = start_h + (float)ph * bin_h;
+    float wf = start_w + (float)pw * bin_w;
+    // malformed ROI (:94-97) or grid point outside the map (:104-108) -> 0
+    const bool zero = (roi_h <= 0.f || roi_w <= 0.f) || hf < -0.5f || (double)hf > (double)H - 0.5 ||
+                      wf < -0.5f || (double)wf > (double)W - 0.5;
+    int h0 = (int)floorf(hf), w0 = (int)floorf(wf);
+    int h1 = h0 + 1, w1 = w0 + 1;
+    hf = fminf(fmaxf(hf, 0.f), (float)(H - 1));
+    wf = fminf(fmaxf(wf, 0.f), (float)(W - 1));
+    h0 = min(max(h0, 0), H - 1); w0 = min(max(w0, 0), W - 1);
+    h1 = min(max(h1, 0), H - 1); w1 = min(max(w1, 0), W - 1);
+    const float lh = hf - (float)h0, lw = wf - (float)w0;
+    const float hh = 1.f - lh, hw = 1.f - lw;
+    const float w00 = hw * hh, w10 = lw * hh, w01 = hw * lh, w11 = lw * lh;
+    const size_t img = (size_t)b * H;
+    for (int g = lane; g < cg; g += 32) {
+      Vec8 r;
+      if (zero) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.v[i] = 0.f;
+      } else {
+        const Vec8 v00 = load8(xh, xl, ((img + h0) * W + w0) * C + g * 8);
+        const Vec8 v10 = load8(xh, xl, ((img + h0) * W + w1) * C + g * 8);
+        const Vec8 v01 = load8(xh, xl, ((img + h1) * W + w0) * C + g * 8);
+        const Vec8 v11 = load8(xh, xl, ((img + h1) * W + w1) * C + g * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)  // :131 left-to-right
+          r.v[i] = ((w00 * v00.v[i] + w10 * v10.v[i]) + w01 * v01.v[i]) + w11 * v11.v[i];
+      }
+      store8(yh, yl, pt * Ctot + c_off + g * 8, r);
+    }
+  }
+}
+
 // ------------------------------------------------------------ depthwise Deconvolution 2x
 // DeconvolutionLayer::Forward_cpu (src/caffe/layers/deconv_layer.cpp:25-40) for the shape the
 // MS-CNN "-2x" nets use: group == channels, kernel 4, stride 2, pad 1, no bias
@@ -313,6 +378,24 @@ extern "C" int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N,
                                       int out_channels_total, int out_channel_offset, void* stream) {
   return mscnn_roi_pool_multi_forward(x_hi, x_lo, N, H, W, C, rois, R, pooled_h, pooled_w, spatial_scale, 1,
                                       &pad_ratio, &out_channel_offset, y_hi, y_lo, out_channels_total, stream);
+}
+
+extern "C" int mscnn_roi_align_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                       const float* rois, int R, int pooled_h, int pooled_w,
+                                       float spatial_scale, float pad_ratio, void* y_hi, void* y_lo,
+                                       int out_channels_total, int out_channel_offset, void* stream) {
+  if (!x_hi || !y_hi || !rois || N <= 0 || H <= 0 || W <= 0 || C % 8 || R < 0 || pooled_h <= 0 || pooled_w <= 0 ||
+      out_channels_total % 8 || out_channel_offset % 8 || out_channel_offset + C > out_channels_total)
+    return MSCNN_ERR_INVALID;
+  if ((x_lo == nullptr) != (y_lo == nullptr)) return MSCNN_ERR_INVALID;
+  if (R == 0) return MSCNN_OK;
+  const size_t total = (size_t)R * (pooled_h + 1) * (pooled_w + 1) * 32;  // one warp per (ROI, grid point)
+  mscnn::note_launch();
+  roi_align_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, rois, R, N, H, W, C, pooled_h, pooled_w,
+      spatial_scale, pad_ratio, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total,
+      out_channel_offset);
+  return launch_check("roi_align");
 }
 
 extern "C" int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const float* w, void* y_hi,

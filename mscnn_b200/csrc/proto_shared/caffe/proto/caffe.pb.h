@@ -255,6 +255,35 @@ class BBoxRegParameter {  // caffe.proto:1346-1350
   PB_OPT(bool, cls_aware, true)
 };
 
+class DecodeBBoxParameter {  // caffe.proto:1353-1355
+  PB_OPT(float, gt_iou_thr, 0.95f)
+};
+
+enum SoftmaxParameter_Engine {
+  SoftmaxParameter_Engine_DEFAULT = 0,
+  SoftmaxParameter_Engine_CAFFE = 1,
+  SoftmaxParameter_Engine_CUDNN = 2
+};
+class SoftmaxParameter {  // caffe.proto:1129-1141
+ public:
+  typedef SoftmaxParameter_Engine Engine;
+  PB_OPT(SoftmaxParameter_Engine, engine, SoftmaxParameter_Engine_DEFAULT)
+  PB_OPT(int32_t, axis, 1)
+};
+
+enum EltwiseParameter_EltwiseOp {
+  EltwiseParameter_EltwiseOp_PROD = 0,
+  EltwiseParameter_EltwiseOp_SUM = 1,
+  EltwiseParameter_EltwiseOp_MAX = 2
+};
+class EltwiseParameter {  // caffe.proto:695-707
+ public:
+  typedef EltwiseParameter_EltwiseOp EltwiseOp;
+  PB_OPT(EltwiseParameter_EltwiseOp, operation, EltwiseParameter_EltwiseOp_SUM)
+  PB_REP(float, coeff)
+  PB_OPT(bool, stable_prod_grad, true)
+};
+
 class LayerParameter {  // caffe.proto:310-414 (fields used by the deploy nets' layer types)
  public:
   void Clear() { *this = LayerParameter(); }
@@ -278,6 +307,9 @@ class LayerParameter {  // caffe.proto:310-414 (fields used by the deploy nets' 
   PB_MSG(ROIPoolingParameter, roi_pooling_param)
   PB_MSG(BoxOutputParameter, box_output_param)
   PB_MSG(BBoxRegParameter, bbox_reg_param)
+  PB_MSG(DecodeBBoxParameter, decode_bbox_param)
+  PB_MSG(SoftmaxParameter, softmax_param)
+  PB_MSG(EltwiseParameter, eltwise_param)
 };
 
 class NetState {  // caffe.proto:257-261

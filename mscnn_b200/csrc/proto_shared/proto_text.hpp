@@ -53,7 +53,7 @@ inline void fill(const Node& n, LayerParameter* lp) {
               {"name", "type", "bottom", "top", "phase", "loss_weight", "param", "propagate_down", "include",
                "exclude", "convolution_param", "pooling_param", "inner_product_param", "input_param",
                "dropout_param", "concat_param", "relu_param", "roi_pooling_param", "box_output_param",
-               "bbox_reg_param"});
+               "bbox_reg_param", "decode_bbox_param", "softmax_param", "eltwise_param"});
   lp->set_name(n.str("name"));
   lp->set_type(n.str("type"));
   for (const std::string& s : n.strs("bottom")) lp->add_bottom(s);
@@ -174,6 +174,26 @@ inline void fill(const Node& n, LayerParameter* lp) {
     for (double v : c->nums("bbox_mean")) p->add_bbox_mean((float)v);
     for (double v : c->nums("bbox_std")) p->add_bbox_std((float)v);
     if (c->has("cls_aware")) p->set_cls_aware(c->boolean("cls_aware", true));
+  }
+  if (const Node* c = n.child("decode_bbox_param")) {
+    check_known(*c, "DecodeBBoxParameter", {"gt_iou_thr"});
+    if (c->has("gt_iou_thr")) lp->mutable_decode_bbox_param()->set_gt_iou_thr((float)c->num("gt_iou_thr", 0.95));
+  }
+  if (const Node* c = n.child("softmax_param")) {
+    check_known(*c, "SoftmaxParameter", {"engine", "axis"});
+    if (c->has("axis")) lp->mutable_softmax_param()->set_axis((int)c->num("axis", 1));
+  }
+  if (const Node* c = n.child("eltwise_param")) {
+    check_known(*c, "EltwiseParameter", {"operation", "coeff", "stable_prod_grad"});
+    EltwiseParameter* p = lp->mutable_eltwise_param();
+    if (c->has("operation")) {
+      const std::string m = c->str("operation");
+      p->set_operation(m == "PROD" ? EltwiseParameter_EltwiseOp_PROD
+                       : m == "MAX" ? EltwiseParameter_EltwiseOp_MAX
+                                    : EltwiseParameter_EltwiseOp_SUM);
+    }
+    for (double v : c->nums("coeff")) p->add_coeff((float)v);
+    if (c->has("stable_prod_grad")) p->set_stable_prod_grad(c->boolean("stable_prod_grad", true));
   }
 }
 

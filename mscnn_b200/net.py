@@ -51,6 +51,9 @@ def _declare(L):
     L.mscnn_net_layer_times.argtypes = [C.c_void_p, C.c_void_p]
     L.mscnn_net_num_proposals.argtypes = [C.c_void_p, C.c_int]
     L.mscnn_net_detect.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_void_p, C.c_void_p]
+    L.mscnn_net_detect_cascade.restype = C.c_int
+    L.mscnn_net_detect_cascade.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_char_p, C.c_char_p, C.c_char_p,
+                                           C.c_void_p, C.c_void_p]
     L.mscnn_set_precision.argtypes = [C.c_int]
     L.mscnn_set_stream.argtypes = [C.c_void_p]
     L.mscnn_set_device.argtypes = [C.c_int]
@@ -207,6 +210,16 @@ class Net:
 
     def detect(self, cfg: capi.DetectCfg, dets_dev_ptr: int, counts_dev_ptr: int) -> None:
         capi.check(self._L.mscnn_net_detect(self._h, cfg, dets_dev_ptr, counts_dev_ptr), "net_detect")
+
+    def detect_cascade(self, cfg: capi.DetectCfg, dets_dev_ptr: int, counts_dev_ptr: int, stage: str = "3rd",
+                       cls_prob: str | None = None) -> None:
+        """Final detections of a cascade net from one stage's blobs (run_cascademscnn.m:36-48):
+        proposals[_2nd|_3rd], cls_prob_<stage> (or e.g. "cls_prob_3rd_avg"), output_bbox_<stage>."""
+        prop = "proposals" if stage == "1st" else f"proposals_{stage}"
+        capi.check(self._L.mscnn_net_detect_cascade(self._h, cfg, prop.encode(),
+                                                    (cls_prob or f"cls_prob_{stage}").encode(),
+                                                    f"output_bbox_{stage}".encode(), dets_dev_ptr, counts_dev_ptr),
+                   "net_detect_cascade")
 
 
 def kitti_detect_cfg(net_h: int, net_w: int, max_rois: int = 2000, num_cls: int = 5, cls_id: int = 2) -> capi.DetectCfg:

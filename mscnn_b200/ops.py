@@ -6,6 +6,7 @@ from __future__ import annotations
 
 from dataclasses import dataclass
 
+import numpy as np
 import torch
 
 from . import capi
@@ -233,6 +234,65 @@ def roi_pool_forward(x: Planes, rois: torch.Tensor, num_rois: int, pooled: int, 
                                                  capi.ptr(out.lo), ctot, channel_offset, _stream()),
                "roi_pool_forward")
     return out
+
+
+def roi_align_forward(x: Planes, rois: torch.Tensor, num_rois: int, pooled: int, scale: float,
+                      pad_ratio: float) -> Planes:
+    """ROIAlign grid [R, pooled+1, pooled+1, C] (roi_align_layer.cpp:49-139)."""
+    n, h, w, c = x.hi.shape
+    y_hi = torch.zeros((num_rois, pooled + 1, pooled + 1, c), dtype=torch.bfloat16, device=x.hi.device)
+    y_lo = torch.zeros_like(y_hi) if x.lo is not None else None
+    out = Planes(y_hi, y_lo, c)
+    capi.check(capi.lib().mscnn_roi_align_forward(capi.ptr(x.hi), capi.ptr(x.lo), n, h, w, c, capi.ptr(rois),
+                                                  num_rois, pooled, pooled, scale, pad_ratio, capi.ptr(out.hi),
+                                                  capi.ptr(out.lo), c, 0, _stream()), "roi_align_forward")
+    return out
+
+
+def decode_bbox_forward(bbox_pred: torch.Tensor, prior: torch.Tensor, mean=None, std=None) -> torch.Tensor:
+    import ctypes as C
+    r = prior.shape[0]
+    out = torch.empty((r, 5), dtype=torch.float32, device=prior.device)
+    m = (C.c_float * 4)(*mean) if mean is not None else None
+    s = (C.c_float * 4)(*std) if std is not None else None
+    capi.check(capi.lib().mscnn_decode_bbox_forward(capi.ptr(bbox_pred), capi.ptr(prior), r, bbox_pred.shape[1],
+                                                    C.cast(m, C.c_void_p), C.cast(s, C.c_void_p), capi.ptr(out),
+                                                    _stream()), "decode_bbox_forward")
+    return out
+
+
+def softmax_forward(x: torch.Tensor, axis: int = 1) -> torch.Tensor:
+    outer = int(np.prod(x.shape[:axis])) if axis > 0 else 1
+    inner = int(np.prod(x.shape[axis + 1:])) if axis + 1 < x.dim() else 1
+    y = torch.empty_like(x)
+    capi.check(capi.lib().mscnn_softmax_forward(capi.ptr(x), outer, x.shape[axis], inner, capi.ptr(y), _stream()),
+               "softmax_forward")
+    return y
+
+
+def eltwise_forward(bottoms: list[torch.Tensor], op: int, coeffs=None) -> torch.Tensor:
+    import ctypes as C
+    y = torch.empty_like(bottoms[0])
+    ptrs = (C.c_void_p * len(bottoms))(*[b.data_ptr() for b in bottoms])
+    cf = (C.c_float * len(bottoms))(*coeffs) if coeffs is not None else None
+    capi.check(capi.lib().mscnn_eltwise_forward(ptrs, len(bottoms), op, C.cast(cf, C.c_void_p), y.numel(),
+                                                capi.ptr(y), _stream()), "eltwise_forward")
+    return y
+
+
+def cascade_detect_postprocess(cfg: capi.DetectCfg, n: int, proposals, cls_prob, output_bbox, num_out):
+    import ctypes as C
+    dev = proposals.device
+    nbytes = C.c_size_t(0)
+    capi.check(capi.lib().mscnn_detect_workspace_bytes(cfg, n, C.byref(nbytes)), "detect_workspace")
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    dets = torch.zeros((n, cfg.max_rois_per_image, 5), dtype=torch.float32, device=dev)
+    counts = torch.zeros(n, dtype=torch.int32, device=dev)
+    capi.check(capi.lib().mscnn_cascade_detect_postprocess(cfg, n, capi.ptr(proposals), capi.ptr(cls_prob),
+                                                           capi.ptr(output_bbox), capi.ptr(num_out), capi.ptr(ws),
+                                                           nbytes.value, capi.ptr(dets), capi.ptr(counts), _stream()),
+               "cascade_detect_postprocess")
+    return dets, counts
 
 
 def detect_postprocess(cfg: capi.DetectCfg, n: int, proposals_score, cls_pred, bbox_pred, num_out):

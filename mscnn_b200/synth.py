@@ -17,7 +17,7 @@ Weights  : per-layer numpy PCG64 stream seeded with 1706 + crc32(layer name):
     s = target_std / sqrt(fan_in * M2_HEAD); background bias +BG_BIAS.  Calibrated once
     (tools/calibrate_synth.py) so that ~3/4 of the anchors pass fg_thr = -5, the top-2000 cap is
     hit, and the dx/dy/dw/dh clamps (box_output_layer.cpp:145-151) trigger on a few percent.
-  * cls_pred / bbox_pred: N(0, target/sqrt(K * M2_FC)), bias 0.
+  * cls_pred* / bbox_pred* (every cascade stage): N(0, target/sqrt(K * M2_FC)), bias 0.
   * Deconvolution (conv4_3_2x): the exact BilinearFiller weights (include/caffe/filler.hpp:248-258).
 """
 from __future__ import annotations
@@ -80,8 +80,8 @@ def make_weights(layers: list[tuple[str, str, list[tuple[int, ...]]]]) -> dict[s
             b = np.zeros(cout, dtype=np.float32)
             b[0] = BG_BIAS
             blobs = [w, b]
-        elif ltype == "InnerProduct" and name in ("cls_pred", "bbox_pred"):
-            std = PRED_CLS_STD if name == "cls_pred" else PRED_BOX_STD
+        elif ltype == "InnerProduct" and name.startswith(("cls_pred", "bbox_pred")):   # incl. cascade stages
+            std = PRED_CLS_STD if name.startswith("cls_pred") else PRED_BOX_STD
             w = (rng.standard_normal(wshape) * (std / np.sqrt(fan_in * M2_FC))).astype(np.float32)
             blobs = [w, np.zeros(wshape[0], dtype=np.float32)]
         else:  # MSRA

@@ -34,6 +34,9 @@ REF_SOURCES = [
     "src/caffe/layers/inner_product_layer.cpp", "src/caffe/layers/dropout_layer.cpp",
     "src/caffe/layers/input_layer.cpp",
     "src/caffe/layers/box_output_layer.cpp", "src/caffe/layers/roi_pooling_layer.cpp",
+    # cascade deploy nets
+    "src/caffe/layers/decode_bbox_layer.cpp", "src/caffe/layers/roi_align_layer.cpp",
+    "src/caffe/layers/softmax_layer.cpp", "src/caffe/layers/eltwise_layer.cpp",
 ]
 OWN_SOURCES = [SHIM / "cblas_shim.cpp", ROOT / "oracle" / "ref_harness.cpp"]
 

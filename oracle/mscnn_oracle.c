@@ -345,3 +345,79 @@ int oracle_bbnms_maxg(const double* bbs, int n, double overlap, int* order) {
   free(ord); free(kp);
   return m;
 }
+
+/*
+ * ROIAlignLayer::Forward_cpu: src/caffe/layers/roi_align_layer.cpp:49-139.  Bilinear samples on
+ * the (ph+1) x (pw+1) grid of bin corners of the padded ROI; malformed ROI or a grid point outside
+ * the map gives 0.  y [rois][channels][ph+1][pw+1].
+ */
+void oracle_roi_align(const float* data, int batch, int channels, int height, int width, const float* rois,
+                      int num_rois, int pooled_h, int pooled_w, float spatial_scale, float pad_ratio, float* y) {
+  const int gh = pooled_h + 1, gw = pooled_w + 1;
+  for (int n = 0; n < num_rois; ++n) {
+    const float* r = rois + (size_t)n * 5;
+    int b = (int)r[0];
+    if (b < 0) b = 0;
+    if (b >= batch) b = batch - 1; /* CHECKed at :63-64 */
+    float pad_w = (r[3] - r[1] + 1) * pad_ratio; /* :67-68 */
+    float pad_h = (r[4] - r[2] + 1) * pad_ratio;
+    float start_w = (r[1] - pad_w) * spatial_scale; /* :71-74 */
+    float start_h = (r[2] - pad_h) * spatial_scale;
+    float end_w = (r[3] + pad_w) * spatial_scale;
+    float end_h = (r[4] + pad_h) * spatial_scale;
+    start_w -= 0.5; start_h -= 0.5; end_w -= 0.5; end_h -= 0.5; /* :77-78 */
+    const float roi_h = end_h - start_h, roi_w = end_w - start_w;
+    const float bin_h = roi_h / (float)pooled_h, bin_w = roi_w / (float)pooled_w;
+    for (int c = 0; c < channels; ++c) {
+      const float* in = data + ((size_t)b * channels + c) * height * width;
+      float* out = y + ((size_t)n * channels + c) * gh * gw;
+      for (int ph = 0; ph < gh; ++ph)
+        for (int pw = 0; pw < gw; ++pw) {
+          float* o = out + ph * gw + pw;
+          if (roi_h <= 0 || roi_w <= 0) { *o = 0; continue; } /* :94-97 */
+          float hf = start_h + (float)ph * bin_h; /* :100-101 */
+          float wf = start_w + (float)pw * bin_w;
+          if (hf < -0.5 || hf > (height - 0.5) || wf < -0.5 || wf > (width - 0.5)) { *o = 0; continue; }
+          int h0 = (int)floorf(hf), w0 = (int)floorf(wf); /* :111-112 */
+          int h1 = h0 + 1, w1 = w0 + 1;
+          hf = fminf(fmaxf(hf, 0.0f), (float)(height - 1)); /* :115-120 */
+          wf = fminf(fmaxf(wf, 0.0f), (float)(width - 1));
+          h0 = h0 < 0 ? 0 : (h0 > height - 1 ? height - 1 : h0);
+          w0 = w0 < 0 ? 0 : (w0 > width - 1 ? width - 1 : w0);
+          h1 = h1 < 0 ? 0 : (h1 > height - 1 ? height - 1 : h1);
+          w1 = w1 < 0 ? 0 : (w1 > width - 1 ? width - 1 : w1);
+          const float lh = hf - h0, lw = wf - w0; /* :123-124 */
+          const float hh = 1 - lh, hw = 1 - lw;
+          const float w00 = hw * hh, w10 = lw * hh, w01 = hw * lh, w11 = lw * lh;
+          const float v00 = in[h0 * width + w0], v10 = in[h0 * width + w1];
+          const float v01 = in[h1 * width + w0], v11 = in[h1 * width + w1];
+          *o = w00 * v00 + w10 * v10 + w01 * v01 + w11 * v11; /* :137 */
+        }
+    }
+  }
+}
+
+/*
+ * DecodeBBoxLayer::Forward_cpu, TEST phase (src/caffe/layers/decode_bbox_layer.cpp:53-124) with
+ * DecodeBBoxesWithPrior (src/caffe/util/math_functions.cpp:46-77): row i of `out` is
+ * [img, x1, y1, x2, y2] of prior i moved by the class-1 deltas bbox[i][4..8).
+ */
+void oracle_decode_bbox(const float* bbox, const float* prior, int num, int bbox_dim, const float* mean,
+                        const float* stdv, float* out) {
+  for (int i = 0; i < num; ++i) {
+    const float* q = prior + (size_t)i * 5;
+    const float xmin = q[1], ymin = q[2], xmax = q[3], ymax = q[4];
+    const float pw = xmax - xmin + 1, ph = ymax - ymin + 1; /* math_functions.cpp:54-55 */
+    const float cx = 0.5 * (xmax + xmin), cy = 0.5 * (ymax + ymin);
+    const float* d = bbox + (size_t)i * bbox_dim + 4; /* class 1: decode_bbox_layer.cpp:115 */
+    const float bx = d[0] * stdv[0] + mean[0], by = d[1] * stdv[1] + mean[1];
+    const float bw = d[2] * stdv[2] + mean[2], bh = d[3] * stdv[3] + mean[3];
+    float tx = bx * pw + cx, ty = by * ph + cy; /* :67-68 */
+    const float tw = pw * expf(bw), th = ph * expf(bh);
+    tx -= (tw - 1) / 2; ty -= (th - 1) / 2;
+    float* o = out + (size_t)i * 5;
+    o[0] = q[0];
+    o[1] = tx; o[2] = ty;
+    o[3] = tx + tw - 1; o[4] = ty + th - 1; /* :72-73 */
+  }
+}

@@ -167,6 +167,60 @@ def roi_pool(x, rois, pooled_h, pooled_w, spatial_scale, pad_ratio=0.0) -> np.nd
     return y
 
 
+def roi_align(x, rois, pooled_h, pooled_w, spatial_scale, pad_ratio=0.0) -> np.ndarray:
+    """ROIAlignLayer::Forward_cpu (roi_align_layer.cpp:49-139) -> [R, C, pooled_h+1, pooled_w+1]."""
+    x, rois = _f32(x), _f32(rois).reshape(-1, 5)
+    n, c, h, w = x.shape
+    r = rois.shape[0]
+    y = np.empty((r, c, pooled_h + 1, pooled_w + 1), dtype=np.float32)
+    lib().oracle_roi_align(C.c_void_p(x.ctypes.data), n, c, h, w, C.c_void_p(rois.ctypes.data), r, pooled_h,
+                           pooled_w, C.c_float(spatial_scale), C.c_float(pad_ratio), C.c_void_p(y.ctypes.data))
+    return y
+
+
+def decode_bbox(bbox_pred, prior, bbox_mean=(0, 0, 0, 0), bbox_std=(1, 1, 1, 1)) -> np.ndarray:
+    """DecodeBBoxLayer::Forward_cpu, TEST phase (decode_bbox_layer.cpp:53-124, math_functions.cpp:46-77)."""
+    b, q = _f32(bbox_pred), _f32(prior).reshape(-1, 5)
+    b = b.reshape(len(q), -1)
+    out = np.empty((len(q), 5), dtype=np.float32)
+    m, sd = _f32(bbox_mean), _f32(bbox_std)
+    lib().oracle_decode_bbox(C.c_void_p(b.ctypes.data), C.c_void_p(q.ctypes.data), len(q), b.shape[1],
+                             C.c_void_p(m.ctypes.data), C.c_void_p(sd.ctypes.data), C.c_void_p(out.ctypes.data))
+    return out
+
+
+def softmax(x, axis=1) -> np.ndarray:
+    """SoftmaxLayer::Forward_cpu (softmax_layer.cpp:28-62): subtract the max, exp (single), divide by the
+    sum.  The reference sums with cblas_sgemv, i.e. in BLAS-defined order; here channel order."""
+    x = _f32(x)
+    m = x.max(axis=axis, keepdims=True)
+    e = np.exp((x - m).astype(np.float64)).astype(np.float32)
+    s = np.zeros_like(m)
+    for k in range(x.shape[axis]):
+        s = (s + np.take(e, [k], axis=axis)).astype(np.float32)
+    return (e / s).astype(np.float32)
+
+
+def eltwise(bottoms, op="SUM", coeffs=None) -> np.ndarray:
+    """EltwiseLayer::Forward_cpu (eltwise_layer.cpp:46-96)."""
+    bs = [_f32(b) for b in bottoms]
+    if op == "PROD":
+        r = bs[0] * bs[1]
+        for b in bs[2:]:
+            r = r * b
+        return r
+    if op == "SUM":
+        cs = [np.float32(1)] * len(bs) if coeffs is None else [np.float32(c) for c in coeffs]
+        r = np.zeros_like(bs[0])
+        for c, b in zip(cs, bs):
+            r = (r + c * b).astype(np.float32)      # caffe_axpy per bottom (:66-68)
+        return r
+    r = np.where(bs[0] > bs[1], bs[0], bs[1])       # :73-80
+    for b in bs[2:]:
+        r = np.where(b > r, b, r)
+    return r
+
+
 def bbnms_maxg(bbs, overlap=0.5) -> np.ndarray:
     """bbNms(bbs,'type','maxg','overlap',o,'ovrDnm','union') -> kept row indices in kept order
     (utils/bbNms.m:75-126)."""
@@ -218,4 +272,33 @@ def detect_postprocess(proposals_score, cls_pred, bbox_pred, cls_id=2, bbox_mean
     th = np.minimum(th, org_h - ty)                                  # :114-115
     bbs = np.stack([tx, ty, tw, th, prob], axis=1).astype(np.float64)
     bbs = bbs[~np.isnan(bbs[:, 4])]                                  # bbNms.m:82 kp = score > -inf
+    return bbs[bbnms_maxg(bbs, overlap)].astype(np.float32)
+
+
+def cascade_detect_postprocess(proposals, cls_prob, output_bbox, cls_id=2, overlap=0.5, ratios=(1.0, 1.0),
+                               org_hw=None, net_hw=None) -> np.ndarray:
+    """The MATLAB post-process of ONE image of the cascade driver
+    (examples/kitti_car/run_cascademscnn.m:99-126): stage blobs proposals [R,5], cls_prob [R,C],
+    output_bbox [R,5] -> final detections [K,5] = [x y w h prob] for class `cls_id` (1-based)."""
+    f = np.float32
+    q = _f32(proposals).reshape(-1, 5)[:, 1:].copy()
+    if len(q) == 0:
+        return np.zeros((0, 5), dtype=np.float32)
+    t = _f32(output_bbox).reshape(len(q), 5)[:, 1:].copy()           # :99-100
+    cls_prob = _f32(cls_prob).reshape(len(q), -1)
+    if org_hw is None:
+        org_hw = net_hw
+    ratio_h, ratio_w = f(ratios[0]), f(ratios[1])
+    org_h, org_w = f(org_hw[0]), f(org_hw[1])
+    t[:, [0, 2]] = t[:, [0, 2]] / ratio_w                             # :101-102
+    t[:, [1, 3]] = t[:, [1, 3]] / ratio_h
+    t[:, [0, 1]] = np.maximum(f(0), t[:, [0, 1]])                     # :104
+    t[:, 2] = np.minimum(t[:, 2], org_w)                              # :105
+    t[:, 3] = np.minimum(t[:, 3], org_h)
+    t[:, [2, 3]] = t[:, [2, 3]] - t[:, [0, 1]] + f(1)                 # :106
+    q[:, [2, 3]] = q[:, [2, 3]] - q[:, [0, 1]] + f(1)                 # :114
+    keep = (q[:, 2] != 0) & (q[:, 3] != 0)                            # :117
+    t, prob = t[keep], cls_prob[keep][:, cls_id - 1]
+    bbs = np.concatenate([t, prob[:, None]], axis=1).astype(np.float64)   # :124, det_thr = -1: no threshold
+    bbs = bbs[~np.isnan(bbs[:, 4])]
     return bbs[bbnms_maxg(bbs, overlap)].astype(np.float32)

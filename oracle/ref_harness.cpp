@@ -24,14 +24,15 @@
 #include "caffe/layers/conv_layer.hpp"
 #include "caffe/layers/pooling_layer.hpp"
 #include "caffe/layers/relu_layer.hpp"
+#include "caffe/layers/softmax_layer.hpp"
 #include "caffe/proto/caffe.pb.h"
 #include "cblas.h"
 #include "proto_text.hpp"
 #include "prototxt.hpp"
 
 namespace caffe {
-// The reference registers these three through layer_factory.cpp (engine dispatch to cuDNN,
-// layer_factory.cpp:36-74,76-112,152-174); with CPU_ONLY the dispatch always lands on the
+// The reference registers these four through layer_factory.cpp (engine dispatch to cuDNN,
+// layer_factory.cpp:36-74,76-112,152-174,199-221); with CPU_ONLY the dispatch always lands on the
 // Caffe-engine classes, which is what these creators return.
 template <typename Dtype>
 shared_ptr<Layer<Dtype> > MscnnRefGetConvolutionLayer(const LayerParameter& p) {
@@ -47,7 +48,12 @@ shared_ptr<Layer<Dtype> > MscnnRefGetReLULayer(const LayerParameter& p) {
 }
 REGISTER_LAYER_CREATOR(Convolution, MscnnRefGetConvolutionLayer);
 REGISTER_LAYER_CREATOR(Pooling, MscnnRefGetPoolingLayer);
+template <typename Dtype>
+shared_ptr<Layer<Dtype> > MscnnRefGetSoftmaxLayer(const LayerParameter& p) {
+  return shared_ptr<Layer<Dtype> >(new SoftmaxLayer<Dtype>(p));
+}
 REGISTER_LAYER_CREATOR(ReLU, MscnnRefGetReLULayer);
+REGISTER_LAYER_CREATOR(Softmax, MscnnRefGetSoftmaxLayer);
 }  // namespace caffe
 
 namespace {
@@ -66,6 +72,7 @@ struct RefLayer {
 struct RefNet {
   std::vector<RefLayer> layers;
   std::map<std::string, std::shared_ptr<Blob<float> > > blobs;
+  std::map<std::string, Blob<float>*> shared_params;
   std::string error;
 
   Blob<float>* blob(const std::string& name) {
@@ -114,6 +121,18 @@ struct RefNet {
       }
       L.layer = caffe::LayerRegistry<float>::CreateLayer(L.param);
       L.layer->SetUp(L.bottom, L.top);
+      // Net::AppendParam (net.cpp:448-538): same non-empty ParamSpec name => ShareData with the owner
+      for (int j = 0; j < (int)L.layer->blobs().size() && j < L.param.param_size(); ++j) {
+        const std::string& pname = L.param.param(j).name();
+        if (pname.empty()) continue;
+        auto owner = shared_params.find(pname);
+        if (owner == shared_params.end()) {
+          shared_params[pname] = L.layer->blobs()[j].get();
+        } else {
+          CHECK(owner->second->shape() == L.layer->blobs()[j]->shape()) << "shared param shape mismatch " << pname;
+          L.layer->blobs()[j]->ShareData(*owner->second);
+        }
+      }
     }
   }
 };

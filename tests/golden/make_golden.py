@@ -9,6 +9,10 @@ Outputs (committed):
                        subsample of conv4_3 / roi_c1 / fc6, per-blob second moments.
   e2e_7s2x_96x320.npz  mscnn-7s-576-2x geometry (Deconvolution + ROI scale 1/4), 1x3x96x320.
   layers.npz           single-layer known-answer vectors for BoxOutput / ROIPooling edge cases.
+  e2e_cascade_kitti_96x320.npz   cascade-mscnn-7s-576-2x geometry, 2x3x96x320: per-stage proposals, class
+                       probabilities, decoded boxes (`python tests/golden/make_golden.py cascade`).
+  e2e_cascade_wider_128x192.npz  cascade-mscnn-12s-align geometry (ROIAlign, shared heads, Eltwise), 2x3x128x192.
+  layers_cascade.npz   single-layer vectors for ROIAlign / DecodeBBox / Softmax / Eltwise edge cases.
 """
 import sys
 from pathlib import Path
@@ -91,5 +95,70 @@ layer { bottom: "x" bottom: "r" top: "c" name: "c" type: "ROIPooling" roi_poolin
     print("layers.npz:", {k: v.shape for k, v in vec.items()})
 
 
+def main_cascade():
+    stages = ["proposals", "proposals_2nd", "proposals_3rd", "output_bbox_1st", "output_bbox_2nd", "output_bbox_3rd",
+              "cls_prob_1st", "cls_prob_2nd", "cls_prob_3rd", "cls_pred", "cls_pred_2nd", "cls_pred_3rd",
+              "bbox_pred", "bbox_pred_2nd", "bbox_pred_3rd", "proposals_score"]
+    g = run_net(models.kitti_cascade(96, 320, batch=2), 2, 96, 320, keep=stages,
+                sub=["conv4_3_2x", "roi_pool", "roi_pool_2nd", "roi_pool_3rd", "fc6", "fc6_2nd", "fc6_3rd"])
+    np.savez_compressed(OUT / "e2e_cascade_kitti_96x320.npz", **g)
+    print("e2e_cascade_kitti_96x320: proposals", g["proposals"].shape)
+    g = run_net(models.widerface_cascade(128, 192, batch=2), 2, 128, 192,
+                keep=stages + ["cls_prob_1st_3rd", "cls_prob_2nd_3rd", "cls_prob_3rd_avg"],
+                sub=["conv4_3", "roi_grid_org", "roi_grid_ctx", "roi_pool", "roi_pool_3rd", "fc6", "fc6_3rd",
+                     "fc6_1st_3rd"])
+    np.savez_compressed(OUT / "e2e_cascade_wider_128x192.npz", **g)
+    print("e2e_cascade_wider_128x192: proposals", g["proposals"].shape)
+
+    rng = np.random.default_rng(1707)
+    vec = {}
+    # ROIAlign: regular / malformed (x2 < x1) / outside the map / sub-pixel / whole-image ROIs, two pad ratios
+    proto = '''input: "x" input_dim: 2 input_dim: 8 input_dim: 12 input_dim: 20
+input: "r" input_dim: 7 input_dim: 5 input_dim: 1 input_dim: 1
+layer { bottom: "x" bottom: "r" top: "o" name: "o" type: "ROIAlign" roi_pooling_param { pooled_w: 5 pooled_h: 5 spatial_scale: 0.125 pad_ratio: 0 } }
+layer { bottom: "x" bottom: "r" top: "c" name: "c" type: "ROIAlign" roi_pooling_param { pooled_w: 5 pooled_h: 5 spatial_scale: 0.125 pad_ratio: 0.25 } }'''
+    net = ref.RefNet(proto, is_path=False)
+    x = rng.standard_normal((2, 8, 12, 20)).astype(np.float32)
+    r = np.array([[0, 1, 1, 10, 10], [1, 50, 40, 30, 20], [0, 300, 300, 400, 400], [1, 3.5, 4.5, 4.5, 5.5],
+                  [0, 0, 0, 159, 95], [1, 20.4, 11.6, 77.5, 60.5], [0, -30, -20, 40, 30]], dtype=np.float32)
+    net.set_blob("x", x)
+    net.set_blob("r", r.reshape(7, 5, 1, 1))
+    net.forward()
+    vec.update(align_x=x, align_r=r, align_org=net.blob("o"), align_ctx=net.blob("c"))
+    # DecodeBBox + Softmax + Eltwise
+    proto = '''input: "b" input_dim: 6 input_dim: 8 input_dim: 1 input_dim: 1
+input: "p" input_dim: 6 input_dim: 5 input_dim: 1 input_dim: 1
+input: "s" input_dim: 6 input_dim: 5
+layer { name: "d" type: "DecodeBBox" bottom: "b" bottom: "p" top: "d" bbox_reg_param { bbox_mean: 0 bbox_mean: 0 bbox_mean: 0 bbox_mean: 0 bbox_std: 0.05 bbox_std: 0.05 bbox_std: 0.1 bbox_std: 0.1 } }
+layer { name: "d0" type: "DecodeBBox" bottom: "b" bottom: "p" top: "d0" }
+layer { name: "sm" type: "Softmax" bottom: "s" top: "sm" softmax_param { axis: 1 } }
+layer { name: "es" type: "Eltwise" bottom: "s" bottom: "sm" bottom: "s" top: "es" eltwise_param { operation: SUM coeff: 0.33333333 coeff: -2 coeff: 0.5 } }
+layer { name: "ep" type: "Eltwise" bottom: "s" bottom: "sm" top: "ep" eltwise_param { operation: PROD } }
+layer { name: "em" type: "Eltwise" bottom: "s" bottom: "sm" bottom: "d1" top: "em" eltwise_param { operation: MAX } }'''
+    proto = proto.replace('input: "s" input_dim: 6 input_dim: 5', 'input: "s" input_dim: 6 input_dim: 5 input_dim: 1 input_dim: 1\n'
+                          'input: "d1" input_dim: 6 input_dim: 5 input_dim: 1 input_dim: 1')
+    net = ref.RefNet(proto, is_path=False)
+    b = (rng.standard_normal((6, 8)) * 2).astype(np.float32)
+    p = np.array([[0, 10, 20, 50, 80], [1, 0, 0, 0, 0], [0, 100.5, 30.25, 90.5, 20.25], [1, -5, -5, 700, 300],
+                  [0, 3, 4, 3, 4], [1, 17.3, 9.9, 64.2, 33.3]], dtype=np.float32)
+    sc = (rng.standard_normal((6, 5)) * 4).astype(np.float32)
+    sc[1] = 0          # uniform
+    sc[2, 3] = 60      # saturating
+    d1 = rng.standard_normal((6, 5)).astype(np.float32)
+    net.set_blob("b", b.reshape(6, 8, 1, 1))
+    net.set_blob("p", p.reshape(6, 5, 1, 1))
+    net.set_blob("s", sc.reshape(6, 5, 1, 1))
+    net.set_blob("d1", d1.reshape(6, 5, 1, 1))
+    net.forward()
+    vec.update(dec_b=b, dec_p=p, dec_out=net.blob("d"), dec_out_nostat=net.blob("d0"), sm_x=sc, sm_y=net.blob("sm"),
+               elt_d1=d1, elt_sum=net.blob("es"), elt_prod=net.blob("ep"), elt_max=net.blob("em"))
+    np.savez_compressed(OUT / "layers_cascade.npz", **vec)
+    print("layers_cascade.npz:", {k: v.shape for k, v in vec.items()})
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "cascade":
+        main_cascade()
+    else:
+        main()
+        main_cascade()

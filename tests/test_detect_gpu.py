@@ -6,6 +6,8 @@ Deconvolution 2x, and the final-detection post-process.  All calls go through th
 Bar: integer / index / ordering results bit-exact; box coordinates within 2 ulp (the device
 evaluates exp() in fp64 and rounds once, the reference calls expf); plane kernels exact when
 inputs are bf16-representable."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 import torch
@@ -245,4 +247,122 @@ def test_detect_postprocess_parity(cuda):
         ref = port.detect_postprocess(prop[sl], cls[sl], bbox[sl], cls_id=2, net_hw=(768, 2560))
         assert dcnt[i] == len(ref), f"image {i}: {dcnt[i]} detections vs oracle {len(ref)}"
         np.testing.assert_allclose(dets[i, : dcnt[i]], ref, rtol=1e-6, atol=1e-6)
+        start += cnt
+
+
+# ------------------------------------------------------------------- cascade-net layers
+@pytest.mark.parametrize("split", [True, False], ids=["split", "bf16"])
+@pytest.mark.parametrize("pad_ratio,scale,pooled", [(0.0, 0.125, 5), (0.25, 0.125, 5), (0.25, 0.25, 7)])
+def test_roi_align_parity(cuda, split, pad_ratio, scale, pooled):
+    """ROIAlign grid samples vs the restated roi_align_layer.cpp:49-139.  The inputs are bf16-exact, the
+    interpolation is fp32 in the reference's order; the only difference is the storage of the result
+    as bf16 planes (hi + lo: 2^-17 relative, hi only: 2^-9)."""
+    from mscnn_b200 import ops
+    rng = np.random.default_rng(23)
+    n, c, h, w = 2, 128, 24, 40
+    x = _bf16_exact(rng.standard_normal((n, c, h, w)).astype(np.float32))
+    img_w, img_h = w / scale, h / scale
+    r = 150
+    x1 = rng.uniform(-30, img_w, r); y1 = rng.uniform(-30, img_h, r)
+    bw = rng.uniform(1, 200, r); bh = rng.uniform(1, 150, r)
+    rois = np.stack([rng.integers(0, n, r), x1, y1, x1 + bw, y1 + bh], axis=1).astype(np.float32)
+    rois[0] = [0, 1, 1, 10, 10]
+    rois[1] = [1, 50, 40, 30, 20]                                        # malformed -> zeros (:94-97)
+    rois[2] = [0, img_w + 100, img_h + 100, img_w + 200, img_h + 200]    # outside -> zeros (:104-108)
+    rois[3] = [1, 3.5, 4.5, 4.5, 5.5]
+    rois[4] = [0, 0, 0, img_w - 1, img_h - 1]
+    ref = port.roi_align(x, rois, pooled, pooled, scale, pad_ratio)
+    xp = ops.nchw_to_planes(torch.from_numpy(x).to(cuda), split)
+    out = ops.roi_align_forward(xp, torch.from_numpy(rois).to(cuda), r, pooled, scale, pad_ratio)
+    got = ops.planes_to_nchw(out).cpu().numpy()
+    assert got.shape == ref.shape == (r, c, pooled + 1, pooled + 1)
+    assert not got[1].any() and not got[2].any()
+    np.testing.assert_allclose(got, ref, rtol=2.0 ** -8 if not split else 2e-5, atol=1e-6)
+    assert np.array_equal(got == 0, ref == 0)
+
+
+def test_decode_bbox_parity(cuda):
+    """DecodeBBox vs the restated decode_bbox_layer.cpp:53-124 / math_functions.cpp:46-77 and the golden
+    vectors from the verbatim reference build: bit-exact."""
+    from mscnn_b200 import ops
+    g = np.load(Path(__file__).resolve().parent / "golden" / "layers_cascade.npz")
+    std = (0.05, 0.05, 0.1, 0.1)
+    got = ops.decode_bbox_forward(torch.from_numpy(g["dec_b"]).to(cuda), torch.from_numpy(g["dec_p"]).to(cuda),
+                                  (0, 0, 0, 0), std).cpu().numpy()
+    assert np.array_equal(got, g["dec_out"].reshape(-1, 5))
+    got = ops.decode_bbox_forward(torch.from_numpy(g["dec_b"]).to(cuda), torch.from_numpy(g["dec_p"]).to(cuda)).cpu().numpy()
+    assert np.array_equal(got, g["dec_out_nostat"].reshape(-1, 5))
+    rng = np.random.default_rng(29)
+    r = 5000
+    x1 = rng.uniform(-50, 2500, r); y1 = rng.uniform(-50, 700, r)
+    prior = np.stack([rng.integers(0, 8, r), x1, y1, x1 + rng.uniform(-10, 500, r), y1 + rng.uniform(-10, 400, r)], 1).astype(np.float32)
+    bbox = (rng.standard_normal((r, 8)) * 3).astype(np.float32)
+    ref = port.decode_bbox(bbox, prior, (0.01, -0.02, 0.0, 0.03), (0.1, 0.1, 0.2, 0.2))
+    got = ops.decode_bbox_forward(torch.from_numpy(bbox).to(cuda), torch.from_numpy(prior).to(cuda),
+                                  (0.01, -0.02, 0.0, 0.03), (0.1, 0.1, 0.2, 0.2)).cpu().numpy()
+    assert np.array_equal(got, ref)
+
+
+def test_softmax_eltwise_parity(cuda):
+    from mscnn_b200 import capi, ops
+    g = np.load(Path(__file__).resolve().parent / "golden" / "layers_cascade.npz")
+    sm = ops.softmax_forward(torch.from_numpy(g["sm_x"]).to(cuda)).cpu().numpy()
+    np.testing.assert_allclose(sm, g["sm_y"].reshape(6, 5), rtol=1e-6, atol=1e-12)
+    rng = np.random.default_rng(31)
+    x = (rng.standard_normal((300, 5, 3, 2)) * 4).astype(np.float32)
+    for axis in (1, 3):
+        got = ops.softmax_forward(torch.from_numpy(x).to(cuda), axis).cpu().numpy()
+        assert np.array_equal(got, port.softmax(x, axis))          # same exp, same summation order
+    a, b, c = (rng.standard_normal((1000, 5)).astype(np.float32) for _ in range(3))
+    da, db, dc = (torch.from_numpy(v).to(cuda) for v in (a, b, c))
+    cf = [0.33333333, -2.0, 0.5]
+    assert np.array_equal(ops.eltwise_forward([da, db, dc], capi.ELTWISE_SUM, cf).cpu().numpy(), port.eltwise([a, b, c], "SUM", cf))
+    assert np.array_equal(ops.eltwise_forward([da, db, dc], capi.ELTWISE_SUM).cpu().numpy(), port.eltwise([a, b, c], "SUM"))
+    assert np.array_equal(ops.eltwise_forward([da, db, dc], capi.ELTWISE_PROD).cpu().numpy(), port.eltwise([a, b, c], "PROD"))
+    assert np.array_equal(ops.eltwise_forward([da, db], capi.ELTWISE_MAX).cpu().numpy(), port.eltwise([a, b], "MAX"))
+    assert np.array_equal(ops.eltwise_forward([da, db, dc], capi.ELTWISE_MAX).cpu().numpy(), port.eltwise([a, b, c], "MAX"))
+    np.testing.assert_allclose(ops.eltwise_forward([torch.from_numpy(g["sm_x"]).to(cuda), torch.from_numpy(sm).to(cuda),
+                                                    torch.from_numpy(g["sm_x"]).to(cuda)], capi.ELTWISE_SUM, cf).cpu().numpy(),
+                               g["elt_sum"].reshape(6, 5), rtol=1e-6, atol=1e-6)
+
+
+def test_cascade_detect_postprocess_parity(cuda):
+    """Cascade final detections (run_cascademscnn.m:99-126) vs the restated MATLAB post-process."""
+    from mscnn_b200 import capi, ops
+    rng = np.random.default_rng(37)
+    n = 3
+    counts = [600, 0, 380]
+    props, outs = [], []
+    for i, cnt in enumerate(counts):
+        x1 = rng.uniform(0, 1800, cnt); y1 = rng.uniform(0, 500, cnt)
+        w = rng.uniform(15, 300, cnt); h = rng.uniform(15, 200, cnt)
+        p = np.stack([np.full(cnt, i), x1, y1, x1 + w, y1 + h], axis=1)
+        props.append(p)
+        o = p.copy()
+        o[:, 1:] += rng.normal(0, 6, (cnt, 4))
+        outs.append(o)
+    prop = np.concatenate(props).astype(np.float32)
+    out = np.concatenate(outs).astype(np.float32)
+    prop[7, 3] = prop[7, 1] - 1            # zero width in the "+1" convention -> dropped (:117)
+    out[9, 1:] = [-40, -10, 2100, 700]     # clipped on all four sides
+    r = len(prop)
+    prob = port.softmax((rng.standard_normal((r, 5)) * 2).astype(np.float32))
+    num_out = np.array([r, r] + counts, dtype=np.int32)
+    cfg = capi.DetectCfg()
+    cfg.num_cls, cfg.cls_id = 5, 2
+    cfg.nms_overlap = 0.5
+    cfg.ratio_h, cfg.ratio_w = 576.0 / 375.0, 1920.0 / 1242.0
+    cfg.org_h, cfg.org_w = 375.0, 1242.0
+    cfg.max_rois_per_image = 2000
+    dets, dcnt = ops.cascade_detect_postprocess(cfg, n, torch.from_numpy(prop).to(cuda), torch.from_numpy(prob).to(cuda),
+                                                torch.from_numpy(out).to(cuda), torch.from_numpy(num_out).to(cuda))
+    torch.cuda.synchronize()
+    dets, dcnt = dets.cpu().numpy(), dcnt.cpu().numpy()
+    start = 0
+    for i, cnt in enumerate(counts):
+        sl = slice(start, start + cnt)
+        ref = port.cascade_detect_postprocess(prop[sl], prob[sl], out[sl], cls_id=2, ratios=(cfg.ratio_h, cfg.ratio_w),
+                                              org_hw=(375.0, 1242.0))
+        assert dcnt[i] == len(ref), (i, dcnt[i], len(ref))
+        assert np.array_equal(dets[i, : dcnt[i]], ref)
         start += cnt

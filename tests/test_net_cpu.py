@@ -107,6 +107,8 @@ def test_unknown_field_is_rejected():
     ("kitti_car/mscnn-7s-576", ("kitti", (576, 1920, 7, False))),
     ("kitti_car/mscnn-7s-576-2x", ("kitti", (576, 1920, 7, True))),
     ("widerface/mscnn-12s-2x", ("widerface", (512, 512))),
+    ("kitti_car/cascade-mscnn-7s-576-2x", ("kitti_cascade", (576, 1920))),
+    ("widerface/cascade-mscnn-12s-align", ("widerface_cascade", (512, 512))),
 ])
 def test_shipped_deploy_files_load_unchanged_and_match_generated(ref_path, gen):
     from mscnn_b200 import models
@@ -119,6 +121,43 @@ def test_shipped_deploy_files_load_unchanged_and_match_generated(ref_path, gen):
     assert shipped.layers() == generated.layers()
     assert [shipped.blob_shape(b) for b in shipped.blob_names] == [generated.blob_shape(b) for b in generated.blob_names]
     assert shipped.layer_param_strings() == generated.layer_param_strings()
+
+
+@pytest.mark.skipif(not REF_EX.exists(), reason="reference tree not mounted")
+def test_every_shipped_deploy_net_loads():
+    """All 23 mscnn_deploy.prototxt files of the reference's model zoo (KITTI car / ped-cyc, Caltech,
+    CityPersons, WIDER FACE, plain and cascade) parse, wire up and shape-infer unchanged."""
+    from mscnn_b200.net import Net
+    files = sorted(REF_EX.glob("*/*/mscnn_deploy.prototxt"))
+    assert len(files) == 23
+    for f in files:
+        net = Net(str(f))
+        assert net.blob_shape("proposals") == (1, 5, 1, 1)      # BoxOutput's dummy reshape
+        assert "data" in net.blob_names
+
+
+def test_params_shared_by_name():
+    """ParamSpec names make layers share one blob (Net::AppendParam, net.cpp:448-538): the cascade
+    nets' third-stage ensemble heads reuse the first- and second-stage weights."""
+    from mscnn_b200 import models
+    from mscnn_b200.net import Net
+    net = Net(models.widerface_cascade(128, 192))
+    w = np.full(net.param_shapes("cls_pred")[0], 0.25, dtype=np.float32)
+    net.set_params({"cls_pred": [w, np.arange(2, dtype=np.float32)]})
+    assert np.array_equal(net.param("cls_pred_1st_3rd", 0), w)
+    assert np.array_equal(net.param("cls_pred_1st_3rd", 1), [0, 1])
+    assert not np.array_equal(net.param("cls_pred_2nd_3rd", 0), w)       # shares with cls_pred_2nd instead
+    net.set_params({"cls_pred_2nd_3rd": [2 * w, np.zeros(2, dtype=np.float32)]})
+    assert np.array_equal(net.param("cls_pred_2nd", 0), 2 * w)
+    # a shape mismatch between sharers is a CHECK failure (net.cpp:497-509): it aborts like Caffe does
+    bad = ('input: "d" input_dim: 1 input_dim: 4 input_dim: 1 input_dim: 1\n'
+           'layer { name: "a" type: "InnerProduct" bottom: "d" top: "a" param { name: "w" } inner_product_param { num_output: 3 } }\n'
+           'layer { name: "b" type: "InnerProduct" bottom: "d" top: "b" param { name: "w" } inner_product_param { num_output: 2 } }\n')
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, "-c", "import sys; from mscnn_b200.net import Net; Net(sys.argv[1])", bad],
+                       capture_output=True, text=True, cwd=str(Path(__file__).resolve().parents[1]))
+    assert r.returncode != 0 and "Cannot share param" in r.stderr
 
 
 def test_synth_is_deterministic_and_name_keyed():

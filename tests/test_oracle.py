@@ -158,6 +158,63 @@ def test_detect_postprocess_basics():
     assert abs(det[0, 4] - np.exp(3) / (np.exp(3) + 4)) < 1e-6
 
 
+# --------------------------------------------------------------------- cascade-net layers
+def test_cascade_layers_golden():
+    """ROIAlign / DecodeBBox / Softmax / Eltwise restatements vs vectors generated from oracle/_ref
+    (tests/golden/make_golden.py cascade): malformed, outside and sub-pixel ROIs, missing statistics,
+    a saturating logit."""
+    g = np.load(GOLD / "layers_cascade.npz")
+    assert np.array_equal(port.roi_align(g["align_x"], g["align_r"], 5, 5, 0.125, 0.0), g["align_org"])
+    assert np.array_equal(port.roi_align(g["align_x"], g["align_r"], 5, 5, 0.125, 0.25), g["align_ctx"])
+    assert np.all(g["align_org"][1] == 0) and np.all(g["align_org"][2] == 0)   # malformed / outside -> zeros
+    std = (0.05, 0.05, 0.1, 0.1)
+    assert np.array_equal(port.decode_bbox(g["dec_b"], g["dec_p"], (0, 0, 0, 0), std), g["dec_out"].reshape(-1, 5))
+    assert np.array_equal(port.decode_bbox(g["dec_b"], g["dec_p"]), g["dec_out_nostat"].reshape(-1, 5))
+    sm = port.softmax(g["sm_x"])
+    np.testing.assert_allclose(sm, g["sm_y"].reshape(6, 5), rtol=1e-6, atol=1e-12)
+    np.testing.assert_allclose(sm.sum(1), 1.0, rtol=1e-6)
+    sm_ref = g["sm_y"].reshape(6, 5)
+    np.testing.assert_allclose(port.eltwise([g["sm_x"], sm_ref, g["sm_x"]], "SUM", [0.33333333, -2, 0.5]),
+                               g["elt_sum"].reshape(6, 5), rtol=1e-6, atol=1e-7)
+    assert np.array_equal(port.eltwise([g["sm_x"], sm_ref], "PROD"), g["elt_prod"].reshape(6, 5))
+    assert np.array_equal(port.eltwise([g["sm_x"], sm_ref, g["elt_d1"]], "MAX"), g["elt_max"].reshape(6, 5))
+
+
+@pytest.mark.parametrize("fixture,stds", [("e2e_cascade_kitti_96x320.npz", None), ("e2e_cascade_wider_128x192.npz", None)])
+def test_cascade_stage_chain_golden(fixture, stds):
+    """The stage-to-stage data flow of the cascade nets restated on the reference's own outputs:
+    proposals_{k+1} = DecodeBBox(bbox_pred_k, proposals_k), cls_prob_k = Softmax(cls_pred_k)."""
+    g = np.load(GOLD / fixture)
+    stds = [(0.1, 0.1, 0.2, 0.2), (0.05, 0.05, 0.1, 0.1), (0.033, 0.033, 0.067, 0.067)]
+    pri = ["proposals", "proposals_2nd", "proposals_3rd"]
+    bb = ["bbox_pred", "bbox_pred_2nd", "bbox_pred_3rd"]
+    cp = ["cls_pred", "cls_pred_2nd", "cls_pred_3rd"]
+    for k, nm in enumerate(["1st", "2nd", "3rd"]):
+        r = len(g[pri[k]])
+        dec = port.decode_bbox(g[bb[k]].reshape(r, -1), g[pri[k]], (0, 0, 0, 0), stds[k])
+        assert np.array_equal(dec, g[f"output_bbox_{nm}"].reshape(r, 5))
+        if k < 2:
+            assert np.array_equal(dec, g[pri[k + 1]].reshape(r, 5))
+        np.testing.assert_allclose(port.softmax(g[cp[k]].reshape(r, -1)), g[f"cls_prob_{nm}"].reshape(r, -1),
+                                   rtol=2e-6, atol=1e-10)
+    if "cls_prob_3rd_avg" in g:
+        avg = port.eltwise([g["cls_prob_1st_3rd"], g["cls_prob_2nd_3rd"], g["cls_prob_3rd"]], "SUM", [0.33333333] * 3)
+        np.testing.assert_allclose(avg, g["cls_prob_3rd_avg"], rtol=1e-6)
+
+
+def test_cascade_detect_postprocess_basics():
+    prop = np.array([[0, 10, 10, 109, 59], [0, 12, 11, 111, 60], [0, 700, 100, 699, 150], [0, 300, 200, 340, 260]],
+                    dtype=np.float32)
+    out = prop.copy()
+    out[3] = [0, -20, 190, 2600, 900]       # clipped to the image
+    prob = np.array([[0.1, 0.9], [0.3, 0.7], [0.2, 0.8], [0.6, 0.4]], dtype=np.float32)
+    det = port.cascade_detect_postprocess(prop, prob, out, cls_id=2, net_hw=(768, 2560))
+    # row 2 dropped (zero width: x2 - x1 + 1 == 0), row 1 suppressed by row 0
+    assert det.shape == (2, 5)
+    np.testing.assert_allclose(det[0], [10, 10, 100, 50, 0.9], atol=1e-6)
+    np.testing.assert_allclose(det[1], [0, 190, 2561, 579, 0.4], atol=1e-6)
+
+
 # ------------------------------------------------------ (c) port vs the verbatim reference build
 needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (needs /root/reference)")
 
@@ -214,3 +271,30 @@ layer { name: "f" type: "InnerProduct" bottom: "p" top: "f" inner_product_param 
     np.testing.assert_allclose(port.deconv_depthwise(c, np.broadcast_to(synth.bilinear_kernel(4), (8, 1, 4, 4)).copy()),
                                net.blob("d"), rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(port.inner_product(net.blob("p"), wf, bf), net.blob("f"), rtol=1e-5, atol=1e-5)
+
+
+@needs_ref
+def test_port_cascade_layers_vs_reference_random():
+    rng = np.random.default_rng(21)
+    n, c, h, w, r = 2, 16, 14, 22, 60
+    proto = f'''input: "x" input_dim: {n} input_dim: {c} input_dim: {h} input_dim: {w}
+input: "r" input_dim: {r} input_dim: 5 input_dim: 1 input_dim: 1
+input: "b" input_dim: {r} input_dim: 8 input_dim: 1 input_dim: 1
+input: "s" input_dim: {r} input_dim: 5 input_dim: 3 input_dim: 2
+layer {{ bottom: "x" bottom: "r" top: "a" name: "a" type: "ROIAlign" roi_pooling_param {{ pooled_w: 7 pooled_h: 4 spatial_scale: 0.25 pad_ratio: 0.125 }} }}
+layer {{ bottom: "b" bottom: "r" top: "d" name: "d" type: "DecodeBBox" bbox_reg_param {{ bbox_mean: 0.1 bbox_mean: -0.1 bbox_mean: 0.05 bbox_mean: 0 bbox_std: 0.1 bbox_std: 0.1 bbox_std: 0.2 bbox_std: 0.2 }} }}
+layer {{ bottom: "s" top: "sm" name: "sm" type: "Softmax" softmax_param {{ axis: 1 }} }}
+layer {{ bottom: "s" top: "sl" name: "sl" type: "Softmax" softmax_param {{ axis: -1 }} }}'''
+    net = ref.RefNet(proto, is_path=False)
+    x = rng.standard_normal((n, c, h, w)).astype(np.float32)
+    x1 = rng.uniform(-10, 80, r); y1 = rng.uniform(-10, 50, r)
+    rois = np.stack([rng.integers(0, n, r), x1, y1, x1 + rng.uniform(-5, 60, r), y1 + rng.uniform(-5, 40, r)], 1).astype(np.float32)
+    b = rng.standard_normal((r, 8)).astype(np.float32)
+    s = (rng.standard_normal((r, 5, 3, 2)) * 3).astype(np.float32)
+    net.set_blob("x", x); net.set_blob("r", rois.reshape(r, 5, 1, 1)); net.set_blob("b", b.reshape(r, 8, 1, 1))
+    net.set_blob("s", s)
+    net.forward()
+    assert np.array_equal(port.roi_align(x, rois, 4, 7, 0.25, 0.125), net.blob("a"))
+    assert np.array_equal(port.decode_bbox(b, rois, (0.1, -0.1, 0.05, 0), (0.1, 0.1, 0.2, 0.2)), net.blob("d").reshape(r, 5))
+    np.testing.assert_allclose(port.softmax(s, 1), net.blob("sm"), rtol=2e-6, atol=1e-10)
+    np.testing.assert_allclose(port.softmax(s, 3), net.blob("sl"), rtol=2e-6, atol=1e-10)
