@@ -322,10 +322,13 @@ def test_cascade_stages_isolated_vs_reference(cuda, kind):
         ok_rows = (err.max(axis=1) <= 1e-3).mean()
         worst[name] = (float(ok_rows), float(err.max()))
         first_stage = name in ("cls_pred", "bbox_pred", "proposals_2nd", "output_bbox_1st", "cls_prob_1st")
-        if kind == "wider":
-            assert ok_rows >= 0.995, (name, worst[name])      # ROIAlign is continuous in the boxes
+        if kind == "wider" or first_stage:
+            # ROIAlign is continuous in the boxes, and the first stage pools the reference's own ROIs:
+            # every row within 1e-3 (measured on B200: <= 1.1e-4)
+            assert ok_rows == 1.0, (name, worst[name])
         else:
-            assert ok_rows >= (0.99 if first_stage else 0.95), (name, worst[name])   # ROIPooling round() flips
+            # later ROIPooling stages round() boxes that carry a 1e-5 error: measured 99.4-99.7 % of rows
+            assert ok_rows >= 0.98, (name, worst[name])
     print(kind, worst)
 
 
