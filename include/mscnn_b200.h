@@ -288,6 +288,41 @@ MSCNN_API int mscnn_cascade_detect_postprocess(const mscnn_detect_cfg* cfg, int 
                                      void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Image pre-processing (the step in front of the path).  Replaces the MATLAB code
+ * before net.forward in examples/kitti_car/run_mscnn_detection.m:64-69 and
+ * examples/widerface/run_mscnn_detection.m:70-86:
+ *   imresize(uint8 image, [out_h out_w]) (bicubic, antialiased, uint8 result) -> channel order [3 2 1]
+ *   (RGB -> BGR) -> single -> minus mean [104 117 123] -> W-fastest planes = the net's `data` blob.
+ * images: uint8 [N][in_h][in_w][3] interleaved (what an image decoder returns), all N of one size;
+ * data: fp32 [N][3][out_h][out_w].  mean[] is indexed by OUTPUT channel (after the swap).
+ * A plan holds the fp64 tap tables of one (in, out) size pair on the device. */
+typedef struct mscnn_preprocess_desc {
+  int in_h, in_w;   /* original image */
+  int out_h, out_w; /* net input */
+  float mean[3];
+  int swap_rb; /* 1: input is RGB (imread), output BGR as the reference nets expect */
+} mscnn_preprocess_desc;
+MSCNN_API int mscnn_preprocess_create(const mscnn_preprocess_desc* d, void** plan);
+MSCNN_API int mscnn_preprocess_destroy(void* plan);
+MSCNN_API int mscnn_preprocess_get_desc(void* plan, mscnn_preprocess_desc* d);
+MSCNN_API int mscnn_preprocess_forward(void* plan, int N, const unsigned char* images /*device*/, float* data,
+                                       void* stream);
+/* Same with HOST images: one async H2D copy of the ORIGINAL uint8 pixels into a staging buffer owned by
+ * the plan (pinned host memory makes it asynchronous), then the kernels. */
+MSCNN_API int mscnn_preprocess_forward_host(void* plan, int N, const unsigned char* host_images, float* data,
+                                            void* stream);
+/* Host-only helpers (no CUDA call; usable on a GPU-less box):
+ * imresize's tap tables for one dimension: returns the tap count P (<= cap_taps) and fills
+ * host_weights / host_indices as [out_len][cap_taps] (0-based indices); mscnn_imresize_taps = P alone. */
+MSCNN_API int mscnn_imresize_taps(int in_len, int out_len);
+MSCNN_API int mscnn_imresize_contributions(int in_len, int out_len, double* host_weights, int* host_indices,
+                                           int cap_taps);
+/* WIDER FACE net input size: round to multiples of 32, cap the longer side at max_size
+ * (examples/widerface/run_mscnn_detection.m:72-80); img_h / img_w = 0 keeps the original size. */
+MSCNN_API int mscnn_widerface_net_size(int org_h, int org_w, int img_h, int img_w, int max_size, int* rz_h,
+                                       int* rz_w);
+
+/* ------------------------------------------------------------------------------------
  * Net facade: caffe::Net<float> of the Caffe-API mirror (mscnn_b200/csrc/caffe_api) for hosts that
  * cannot include C++ headers.  Mirrors what matcaffe / pycaffe expose of Net
  * (/root/reference/matlab/+caffe/private/caffe_.cpp, python/caffe/_caffe.cpp):
@@ -322,6 +357,9 @@ MSCNN_API int mscnn_net_set_blob(void* net, const char* blob, const float* host,
 MSCNN_API int mscnn_net_set_blob_device(void* net, const char* blob, const float* dev, long count); /* async D2D */
 MSCNN_API int mscnn_net_get_blob(void* net, const char* blob, float* host, long count);             /* D2H + sync */
 MSCNN_API const float* mscnn_net_blob_device(void* net, const char* blob);
+/* uint8 host images -> pre-processing kernels -> the input blob (N, in size and out size from the plan / blob). */
+MSCNN_API int mscnn_net_set_input_images(void* net, const char* blob, void* preprocess_plan, int N,
+                                         const unsigned char* host_images);
 MSCNN_API int mscnn_net_forward(void* net, int from_layer, int to_layer); /* inclusive; to < 0 = last */
 MSCNN_API int mscnn_net_set_layer_timing(void* net, int on);
 MSCNN_API int mscnn_net_layer_times(void* net, float* ms);                 /* ms per layer, last forward */

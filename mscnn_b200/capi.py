@@ -69,6 +69,11 @@ class DetectCfg(C.Structure):
     ]
 
 
+class PreprocessDesc(C.Structure):
+    _fields_ = [("in_h", c_int), ("in_w", c_int), ("out_h", c_int), ("out_w", c_int), ("mean", c_float * 3),
+                ("swap_rb", c_int)]
+
+
 _lib = None
 
 
@@ -134,6 +139,22 @@ def _declare(L: C.CDLL) -> None:
     L.mscnn_detect_postprocess.restype = c_int
     L.mscnn_detect_postprocess.argtypes = [C.POINTER(DetectCfg), c_int] + [c_void_p] * 5 + [C.c_size_t] + \
         [c_void_p] * 3
+
+
+    L.mscnn_preprocess_create.restype = c_int
+    L.mscnn_preprocess_create.argtypes = [C.POINTER(PreprocessDesc), C.POINTER(c_void_p)]
+    L.mscnn_preprocess_destroy.argtypes = [c_void_p]
+    L.mscnn_preprocess_get_desc.argtypes = [c_void_p, C.POINTER(PreprocessDesc)]
+    L.mscnn_preprocess_forward.restype = c_int
+    L.mscnn_preprocess_forward.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.mscnn_preprocess_forward_host.restype = c_int
+    L.mscnn_preprocess_forward_host.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p]
+    L.mscnn_imresize_taps.restype = c_int
+    L.mscnn_imresize_taps.argtypes = [c_int, c_int]
+    L.mscnn_imresize_contributions.restype = c_int
+    L.mscnn_imresize_contributions.argtypes = [c_int, c_int, c_void_p, c_void_p, c_int]
+    L.mscnn_widerface_net_size.restype = c_int
+    L.mscnn_widerface_net_size.argtypes = [c_int] * 5 + [C.POINTER(c_int)] * 2
 
 
 def check(rc: int, what: str = "") -> None:

@@ -179,6 +179,15 @@ int mscnn_net_set_blob(void* h, const char* name, const float* host, long count)
              ? MSCNN_OK
              : MSCNN_ERR_CUDA;
 }
+// uint8 host images -> device pre-processing -> input blob (run_mscnn_detection.m:64-69 on the device)
+int mscnn_net_set_input_images(void* h, const char* name, void* plan, int N, const unsigned char* host_images) {
+  if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
+  mscnn_preprocess_desc d;
+  if (mscnn_preprocess_get_desc(plan, &d) != MSCNN_OK) return MSCNN_ERR_INVALID;
+  Blob<float>* b = H(h)->net->blob_by_name(name).get();
+  if (b->count() != (long)N * 3 * d.out_h * d.out_w) return MSCNN_ERR_INVALID;
+  return mscnn_preprocess_forward_host(plan, N, host_images, b->mutable_gpu_data(), Caffe::stream());
+}
 int mscnn_net_set_blob_device(void* h, const char* name, const float* dev, long count) {
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   Blob<float>* b = H(h)->net->blob_by_name(name).get();

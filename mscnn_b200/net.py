@@ -42,6 +42,7 @@ def _declare(L):
     L.mscnn_net_blob_shape.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
     L.mscnn_net_reshape_blob.argtypes = [C.c_void_p, C.c_char_p] + [C.c_int] * 4
     L.mscnn_net_set_blob.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
+    L.mscnn_net_set_input_images.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]
     L.mscnn_net_set_blob_device.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
     L.mscnn_net_get_blob.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
     L.mscnn_net_blob_device.restype = C.c_void_p
@@ -185,6 +186,16 @@ class Net:
         return p
 
     # ---- execution -----------------------------------------------------------------------
+    def set_input_images(self, name: str, pre, images) -> None:
+        """uint8 host images [N][h][w][3] (numpy or pinned CPU tensor) -> device pre-processing (`pre` = an
+        ops.Preprocess plan) -> the input blob; the MATLAB code before net.forward, run_mscnn_detection.m:64-69."""
+        n = images.shape[0]
+        shp = (n, 3, *pre.out_hw)
+        if self.blob_shape(name) != shp:
+            capi.check(self._L.mscnn_net_reshape_blob(self._h, name.encode(), *shp), "reshape_blob")
+        capi.check(self._L.mscnn_net_set_input_images(self._h, name.encode(), pre.handle, n, capi.ptr(images)),
+                   "set_input_images")
+
     def forward_only(self, start: str | None = None, end: str | None = None) -> None:
         i0 = self.layer_names.index(start) if start else 0
         i1 = self.layer_names.index(end) if end else -1

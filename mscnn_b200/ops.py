@@ -321,3 +321,57 @@ def conv3x3_c3_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None,
                                                    capi.ptr(y_lo), n, h, wd, cout, cp, int(relu), _stream()),
                "conv3x3_c3_forward")
     return Planes(y_hi, y_lo, cout)
+
+
+# ---- pre-processing ------------------------------------------------------------
+def imresize_contributions(in_len: int, out_len: int) -> tuple[np.ndarray, np.ndarray]:
+    """The library's imresize tap tables for one dimension (host-only call, works without a GPU)."""
+    L = capi.lib()
+    taps = L.mscnn_imresize_taps(in_len, out_len)
+    capi.check(min(taps, 0), "imresize_taps")
+    w = np.zeros((out_len, taps), dtype=np.float64)
+    idx = np.zeros((out_len, taps), dtype=np.int32)
+    rc = L.mscnn_imresize_contributions(in_len, out_len, w.ctypes.data, idx.ctypes.data, taps)
+    capi.check(min(rc, 0), "imresize_contributions")
+    return w, idx
+
+
+def widerface_net_size(org_h: int, org_w: int, img_h: int = 0, img_w: int = 0, max_size: int = 2048) -> tuple[int, int]:
+    import ctypes as C
+    h, w = C.c_int(), C.c_int()
+    capi.check(capi.lib().mscnn_widerface_net_size(org_h, org_w, img_h, img_w, max_size, C.byref(h), C.byref(w)),
+               "widerface_net_size")
+    return h.value, w.value
+
+
+class Preprocess:
+    """imresize + BGR + mean subtraction + CHW on the device for images of one size
+    (examples/kitti_car/run_mscnn_detection.m:64-69)."""
+
+    def __init__(self, in_hw, out_hw, mean=(104.0, 117.0, 123.0), swap_rb=True):
+        import ctypes as C
+        d = capi.PreprocessDesc(in_hw[0], in_hw[1], out_hw[0], out_hw[1], (C.c_float * 3)(*mean), int(swap_rb))
+        h = C.c_void_p()
+        capi.check(capi.lib().mscnn_preprocess_create(C.byref(d), C.byref(h)), "preprocess_create")
+        self.handle, self.in_hw, self.out_hw = h, tuple(in_hw), tuple(out_hw)
+
+    def __del__(self):
+        if getattr(self, "handle", None):
+            capi.lib().mscnn_preprocess_destroy(self.handle)
+            self.handle = None
+
+    def __call__(self, images, out: torch.Tensor | None = None) -> torch.Tensor:
+        """images: uint8 [N][h][w][3], a torch.cuda tensor, or a host numpy array / CPU tensor (H2D inside)."""
+        n = images.shape[0]
+        assert tuple(images.shape[1:]) == (*self.in_hw, 3) and images.dtype in (torch.uint8, np.uint8)
+        if out is None:
+            out = torch.empty((n, 3, *self.out_hw), dtype=torch.float32, device="cuda")
+        L = capi.lib()
+        if isinstance(images, torch.Tensor) and images.is_cuda:
+            assert images.is_contiguous()
+            capi.check(L.mscnn_preprocess_forward(self.handle, n, capi.ptr(images), capi.ptr(out), _stream()),
+                       "preprocess_forward")
+        else:
+            capi.check(L.mscnn_preprocess_forward_host(self.handle, n, capi.ptr(images), capi.ptr(out), _stream()),
+                       "preprocess_forward_host")
+        return out

@@ -302,3 +302,98 @@ def cascade_detect_postprocess(proposals, cls_prob, output_bbox, cls_id=2, overl
     bbs = np.concatenate([t, prob[:, None]], axis=1).astype(np.float64)   # :124, det_thr = -1: no threshold
     bbs = bbs[~np.isnan(bbs[:, 4])]
     return bbs[bbnms_maxg(bbs, overlap)].astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Pre-processing in front of net.forward: examples/kitti_car/run_mscnn_detection.m:64-69,
+# examples/widerface/run_mscnn_detection.m:70-86.  `imresize` is MathWorks code that is NOT part of the reference
+# repository; what follows restates its published algorithm (imresize.m: `contributions`, `cubic`; resize order by
+# ascending scale; per-pass saturating round for integer images).  PARITY UNPINNED against MATLAB itself (no
+# MATLAB / Octave here); tests/test_oracle.py cross-checks the tap tables against torch's antialiased bicubic
+# (same a = -0.5 kernel, same support widening) on float data.
+def _cubic(x: np.ndarray) -> np.ndarray:
+    a = np.abs(x)
+    a2 = a * a
+    a3 = a2 * a
+    f1 = (1.5 * a3 - 2.5 * a2) + 1.0
+    f2 = ((-0.5 * a3 + 2.5 * a2) - 4.0 * a) + 2.0
+    return np.where(a <= 1.0, f1, np.where(a <= 2.0, f2, 0.0))
+
+
+def imresize_contributions(in_len: int, out_len: int) -> tuple[np.ndarray, np.ndarray]:
+    """(weights fp64 [out][P], indices int [out][P], 0-based) of imresize.m's `contributions` for the bicubic
+    kernel with antialiasing (the defaults of `imresize(img, [H W])`)."""
+    scale = float(out_len) / float(in_len)
+    aa = scale < 1.0
+    kw = 4.0 / scale if aa else 4.0
+    x = np.arange(1, out_len + 1, dtype=np.float64)
+    u = x / scale + 0.5 * (1.0 - 1.0 / scale)
+    left = np.floor(u - kw / 2.0)
+    P = int(np.ceil(kw)) + 2
+    ind = left[:, None] + np.arange(P, dtype=np.float64)[None, :]          # 1-based positions
+    d = u[:, None] - ind
+    w = scale * _cubic(scale * d) if aa else _cubic(d)
+    s = np.zeros(out_len)
+    for k in range(P):                                                       # sequential row sum
+        s = s + w[:, k]
+    w = w / s[:, None]
+    m = np.mod(ind.astype(np.int64) - 1, 2 * in_len)                          # aux = [1:in, in:-1:1]
+    idx = np.where(m < in_len, m, 2 * in_len - 1 - m)
+    keep = np.any(w != 0.0, axis=0)
+    return np.ascontiguousarray(w[:, keep]), np.ascontiguousarray(idx[:, keep]).astype(np.int32)
+
+
+def _round_half_away(v: np.ndarray) -> np.ndarray:
+    f = np.floor(v)
+    return np.where(v - f >= 0.5, f + 1.0, f)
+
+
+def _resize_along(img: np.ndarray, dim: int, w: np.ndarray, idx: np.ndarray, to_u8: bool) -> np.ndarray:
+    src = img.astype(np.float64)
+    out_len, P = w.shape
+    shape = list(src.shape)
+    shape[dim] = out_len
+    acc = np.zeros(shape)
+    for k in range(P):                                                       # tap order = table order
+        taps = np.take(src, idx[:, k], axis=dim)
+        wk = w[:, k].reshape([-1 if a == dim else 1 for a in range(src.ndim)])
+        acc = acc + wk * taps
+    if to_u8:
+        acc = _round_half_away(np.clip(acc, 0.0, 255.0)).astype(np.uint8)
+    return acc
+
+
+def imresize(img: np.ndarray, out_hw: tuple[int, int]) -> np.ndarray:
+    """imresize(img, [H W]) for an H x W x C image: uint8 in -> uint8 out (rounded after each pass); float in ->
+    float64 out (no rounding)."""
+    to_u8 = img.dtype == np.uint8
+    tabs = [imresize_contributions(img.shape[k], out_hw[k]) for k in range(2)]
+    scales = [out_hw[k] / img.shape[k] for k in range(2)]
+    order = [0, 1] if scales[0] <= scales[1] else [1, 0]                    # sort(scale), stable
+    out = img
+    for dim in order:
+        out = _resize_along(out, dim, tabs[dim][0], tabs[dim][1], to_u8)
+    return out
+
+
+def preprocess(img_rgb_u8: np.ndarray, net_hw: tuple[int, int], mean_bgr=(104.0, 117.0, 123.0)) -> np.ndarray:
+    """run_mscnn_detection.m:64-69: uint8 H x W x 3 RGB image -> fp32 3 x netH x netW (BGR, mean-subtracted)."""
+    r = imresize(img_rgb_u8, net_hw)
+    bgr = r[:, :, ::-1].astype(np.float32)
+    bgr = bgr - np.asarray(mean_bgr, dtype=np.float32)[None, None, :]
+    return np.ascontiguousarray(bgr.transpose(2, 0, 1))
+
+
+def widerface_net_size(org_h: int, org_w: int, img_h: int = 0, img_w: int = 0, max_size: int = 2048) -> tuple[int, int]:
+    """examples/widerface/run_mscnn_detection.m:72-80."""
+    def rnd(v):
+        return float(np.floor(v + 0.5))
+    w = float(org_w if img_w == 0 else img_w)
+    h = float(org_h if img_h == 0 else img_h)
+    w = rnd(w / 32.0) * 32.0
+    h = rnd(h / 32.0) * 32.0
+    if h > max_size or w > max_size:
+        r = max_size / max(h, w)
+        h = rnd(h * r / 32.0) * 32.0
+        w = rnd(w * r / 32.0) * 32.0
+    return int(h), int(w)
