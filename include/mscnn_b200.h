@@ -323,6 +323,31 @@ MSCNN_API int mscnn_widerface_net_size(int org_h, int org_w, int img_h, int img_
                                        int* rz_w);
 
 /* ------------------------------------------------------------------------------------
+ * KITTI result writer / evaluator glue (the step behind the path).  Host-only: plain
+ * files in, plain files out, no CUDA call (usable on a GPU-less box), as in the reference, where these are
+ * MATLAB scripts and a stand-alone C++ tool.
+ *
+ * mscnn_kitti_write_det_file: examples/kitti_car/run_mscnn_detection.m:150-161 -- one text row
+ *   "img,x,y,w,h,score" per final detection (dlmwrite defaults: ',' and %.5g); host_dets [N][max_rois][5] and
+ *   host_counts [N] are HOST copies of mscnn_detect_postprocess's outputs, img = first_image_index + n (1-based
+ *   position in the image list).
+ * mscnn_kitti_write_labels: examples/kitti_result/writeDetForEval.m:19-95 -- reads up to three such files
+ *   (NULL or missing = no detections of that class), and writes <save_dir>/<%06d image id>.txt in the KITTI
+ *   label format (x2 = x + w, y2 = y + h, score * score_scale; reference: 1000).
+ * mscnn_kitti_evaluate: examples/kitti_result/eval/evaluate_object.cpp (main -> eval): reads
+ *   <gt_dir>/<id>.txt and <result_dir>/data/<id>.txt for every id in list_path and writes
+ *   <result_dir>/stats_<class>_detection.txt and <result_dir>/plot/<class>_detection.txt byte-identical to the
+ *   reference tool (the gnuplot / pdf calls are not reproduced).  ap (may be NULL) receives
+ *   [car, pedestrian, cyclist] x [easy, moderate, hard] 11-point AP in percent as writeDetForEval.m:104-108
+ *   computes it, or -1 for a class without detections.  Unlike the reference tool, a missing file returns
+ *   MSCNN_ERR_INVALID instead of deleting result_dir. */
+MSCNN_API int mscnn_kitti_write_det_file(const char* path, int N, const float* host_dets, const int* host_counts,
+                                         int max_rois, int first_image_index, int append);
+MSCNN_API int mscnn_kitti_write_labels(const char* car_det_file, const char* ped_det_file, const char* cyc_det_file,
+                                       const char* list_path, const char* save_dir, double score_scale);
+MSCNN_API int mscnn_kitti_evaluate(const char* gt_dir, const char* result_dir, const char* list_path, double* ap);
+
+/* ------------------------------------------------------------------------------------
  * Net facade: caffe::Net<float> of the Caffe-API mirror (mscnn_b200/csrc/caffe_api) for hosts that
  * cannot include C++ headers.  Mirrors what matcaffe / pycaffe expose of Net
  * (/root/reference/matlab/+caffe/private/caffe_.cpp, python/caffe/_caffe.cpp):

@@ -157,6 +157,14 @@ def _declare(L: C.CDLL) -> None:
     L.mscnn_widerface_net_size.argtypes = [c_int] * 5 + [C.POINTER(c_int)] * 2
 
 
+    L.mscnn_kitti_write_det_file.restype = c_int
+    L.mscnn_kitti_write_det_file.argtypes = [C.c_char_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int]
+    L.mscnn_kitti_write_labels.restype = c_int
+    L.mscnn_kitti_write_labels.argtypes = [C.c_char_p] * 5 + [C.c_double]
+    L.mscnn_kitti_evaluate.restype = c_int
+    L.mscnn_kitti_evaluate.argtypes = [C.c_char_p] * 3 + [c_void_p]
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != OK:
         raise MscnnError(f"{what or 'mscnn call'} failed with status {rc}")

@@ -50,7 +50,26 @@ def available() -> bool:
     return LIB.exists()
 
 
+KITTI_EVAL_SRC = REF / "examples" / "kitti_result" / "eval" / "evaluate_object.cpp"
+KITTI_EVAL_BIN = OUT / "evaluate_object"
+
+
+def build_kitti_eval(force: bool = False) -> Path | None:
+    """The reference's KITTI evaluation tool (examples/kitti_result/eval/evaluate_object.cpp), a stand-alone
+    program with no dependency beyond libstdc++: compiled verbatim from where it lies."""
+    if not KITTI_EVAL_SRC.exists():
+        return KITTI_EVAL_BIN if KITTI_EVAL_BIN.exists() else None
+    if KITTI_EVAL_BIN.exists() and not force and KITTI_EVAL_SRC.stat().st_mtime <= KITTI_EVAL_BIN.stat().st_mtime:
+        return KITTI_EVAL_BIN
+    OUT.mkdir(parents=True, exist_ok=True)
+    r = subprocess.run(["g++", "-O2", "-w", "-o", str(KITTI_EVAL_BIN), str(KITTI_EVAL_SRC)], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed on evaluate_object.cpp:\n" + r.stderr[-4000:])
+    return KITTI_EVAL_BIN
+
+
 def build(force: bool = False) -> Path | None:
+    build_kitti_eval(force)
     if not REF.exists():
         return LIB if LIB.exists() else None
     srcs = [REF / s for s in REF_SOURCES] + OWN_SOURCES

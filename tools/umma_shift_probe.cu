@@ -3,6 +3,9 @@
 // horizontally shifted taps of a convolution?  For each row shift s the MMA is issued with the
 // descriptor start address advanced by s*128 B and (a) base_offset = 0, (b) base_offset = s & 7;
 // the 128x64 result is compared with A[s:s+128] * B^T computed on the host.
+// Second question (sbo_rows = 10, 12): may the stride between the 8-row groups (SBO) differ from 1024 B, so
+// that the groups are the 8-pixel rows of a halo tile (8 + 2) pixels wide and ONE TMA-loaded halo tile
+// (10 x 18 pixels) serves all nine taps of a 3x3 convolution over an 8 x 16 pixel output tile?
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O2 -I mscnn_b200/csrc -I include tools/umma_shift_probe.cu \
 //        mscnn_b200/csrc/tmap.cu -o gpurun_out/umma_shift_probe     (run on the GPU box)
@@ -20,12 +23,12 @@
 
 using namespace mscnn;
 
-constexpr int kRowsA = 144;  // 128 + up to 16 rows of shift
+constexpr int kRowsA = 192;  // 16 groups x 10 rows + up to 22 rows of shift, <= 24 KB
 constexpr int kN = 64;
 
 __global__ void __launch_bounds__(128, 1)
 probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int shift,
-             int base_offset, float* __restrict__ out) {
+             int base_offset, int sbo_rows, float* __restrict__ out) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = base, sB = base + 24 * 1024, sBar = sB + 8 * 1024, sTm = sBar + 16;
@@ -56,6 +59,10 @@ probe_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (ptx::elect_one()) {
       uint64_t a_desc = ptx::umma_desc_sw128(sA + shift * 128);
       a_desc |= static_cast<uint64_t>(base_offset & 7) << 49;
+      // stride between 8-row groups: 1024 B in the canonical layout; (8 + 2) * 128 B when the groups are
+      // the 8-pixel rows of a halo tile that is 10 pixels wide
+      a_desc &= ~(static_cast<uint64_t>(0x3FFF) << 32);
+      a_desc |= static_cast<uint64_t>((sbo_rows * 128) >> 4) << 32;
       const uint64_t b_desc = ptx::umma_desc_sw128(sB);
       const uint32_t idesc = ptx::umma_idesc_bf16(128, kN);
       for (int k = 0; k < 4; ++k) ptx::umma_bf16(tmem, a_desc + 2u * k, b_desc + 2u * k, idesc, k ? 1u : 0u);
@@ -93,25 +100,28 @@ int main() {
   if (tmap_2d_bf16(&tmA, dA, 64, kRowsA, 64, kRowsA) || tmap_2d_bf16(&tmB, dB, 64, kN, 64, kN)) return 1;
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 1024);
   std::vector<float> hO(128 * kN);
-  for (int shift = 0; shift <= 10; ++shift) {
+  for (int sbo_rows = 8; sbo_rows <= 12; sbo_rows += 2)
+  for (int shift = 0; shift <= (sbo_rows == 8 ? 10 : 22); ++shift) {
+    if (15 * sbo_rows + 7 + shift >= kRowsA) continue;
     for (int variant = 0; variant < 2; ++variant) {
       const int bo = variant ? (shift & 7) : 0;
       cudaMemset(dO, 0, 128 * kN * 4);
-      probe_kernel<<<1, 128, 40 * 1024>>>(tmA, tmB, shift, bo, dO);
+      probe_kernel<<<1, 128, 40 * 1024>>>(tmA, tmB, shift, bo, sbo_rows, dO);
       cudaError_t e = cudaDeviceSynchronize();
-      if (e != cudaSuccess) { printf("shift %d base_offset %d: CUDA error %s\n", shift, bo, cudaGetErrorString(e)); return 2; }
+      if (e != cudaSuccess) { printf("sbo %d shift %d base_offset %d: CUDA error %s\n", sbo_rows, shift, bo, cudaGetErrorString(e)); return 2; }
       cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost);
       int bad = 0;
       double maxerr = 0;
       for (int r = 0; r < 128; ++r)
         for (int n = 0; n < kN; ++n) {
           double ref = 0;
-          for (int k = 0; k < 64; ++k) ref += (double)fA[(r + shift) * 64 + k] * fB[n * 64 + k];
+          const int src = (r / 8) * sbo_rows + (r % 8) + shift;
+          for (int k = 0; k < 64; ++k) ref += (double)fA[src * 64 + k] * fB[n * 64 + k];
           const double err = fabs(ref - hO[r * kN + n]);
           if (err > 1e-3) ++bad;
           if (err > maxerr) maxerr = err;
         }
-      printf("shift %2d base_offset %d: %s (bad %d / %d, max err %.4f)\n", shift, bo, bad ? "MISMATCH" : "ok", bad, 128 * kN, maxerr);
+      printf("sbo_rows %2d shift %2d base_offset %d: %s (bad %d / %d, max err %.4f)\n", sbo_rows, shift, bo, bad ? "MISMATCH" : "ok", bad, 128 * kN, maxerr);
     }
   }
   return 0;
