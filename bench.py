@@ -241,11 +241,26 @@ def main() -> None:
         net.detect(cfg, dets.data_ptr(), cnt.data_ptr())
         gather()
 
-    def step_e2e():
+    def step_e2e_serial():
         net.set_input("data", host_img)         # pinned host -> device, async on the net stream
         net.forward_only()
         net.detect(cfg, dets.data_ptr(), cnt.data_ptr())
         gather()
+        host_dets.copy_(dets, non_blocking=True)
+        host_cnt.copy_(cnt, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def step_e2e():
+        # Software-pipelined over steps, as a throughput deployment feeds the net: every step still does one
+        # H2D upload of a full input batch from pinned host memory and one D2H read of its detections, but the
+        # upload is the NEXT step's input, issued on the copy stream as soon as this step's forward has been
+        # queued (it starts on the device once conv1_1 of this step has consumed the blob), so it overlaps the
+        # ROI head instead of preceding the trunk.  The first timed step's input was uploaded by the last
+        # warm-up step; K timed steps contain exactly K uploads and K downloads.
+        net.forward_only()
+        net.detect(cfg, dets.data_ptr(), cnt.data_ptr())
+        gather()
+        net.set_input_async("data", host_img)
         host_dets.copy_(dets, non_blocking=True)
         host_cnt.copy_(cnt, non_blocking=True)
         torch.cuda.current_stream().synchronize()
@@ -294,6 +309,8 @@ def main() -> None:
         props = torch.tensor([float(net.num_proposals())], device=dev)
         if world > 1:
             dist.all_reduce(props)
+        ms_e2e_serial = timed(step_e2e_serial, args.steps, args.warmup)
+        net.set_input_async("data", host_img)   # prologue of the pipelined loop
         ms_e2e = timed(step_e2e, args.steps, args.warmup)
         # per-layer device times for the roofline: two extra forwards with CUDA events per layer
         mnet.set_precision(mode)
@@ -303,7 +320,7 @@ def main() -> None:
         conv_ms = sum(min(lt[k], lt2[k]) for k in lt if types[k] in ("Convolution", "InnerProduct"))
         all_ms = sum(min(lt[k], lt2[k]) for k in lt)
         flops, conv_launches = conv_flops(net, B)
-        results[mode] = dict(ms=ms, ms_e2e=ms_e2e, props=float(props.item()), conv_ms=conv_ms, all_ms=all_ms,
+        results[mode] = dict(ms=ms, ms_e2e=ms_e2e, ms_e2e_serial=ms_e2e_serial, props=float(props.item()), conv_ms=conv_ms, all_ms=all_ms,
                              flops=flops, conv_launches=conv_launches, clocks=clocks, launched=launched,
                              top=sorted(((min(lt[k], lt2[k]), k) for k in lt), reverse=True)[:6],
                              layers={k: round(min(lt[k], lt2[k]), 3) for k in lt if min(lt[k], lt2[k]) >= 0.02})
@@ -334,7 +351,12 @@ def main() -> None:
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": r["ms_e2e"] / args.steps,
                 "h2d_bytes_per_step": B * 3 * NET_H * NET_W * 4 * world,
                 "d2h_bytes_per_step": (B * cap * 5 * 4 + B * 4) * world,
-                "api": "mscnn_b200.net.Net.set_input(pinned host) / forward_only / detect + D2H of detections"},
+                "serial_value": total_images / (r["ms_e2e_serial"] / 1e3),
+                "serial_ms_per_step": r["ms_e2e_serial"] / args.steps,
+                "api": "mscnn_b200.net.Net: forward_only / detect / set_input_async(pinned host, next step's batch, "
+                       "copy stream) / D2H of detections + sync, software-pipelined over steps (one full-batch upload "
+                       "and one download inside every timed step); serial_* = set_input / forward / detect / D2H "
+                       "strictly in order on one stream"},
         # counted by the library itself (mscnn_kernel_launch_count) inside the timed resident region, all ranks
         "gpu_launches": r["launched"],
         "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel<BLOCK_N> (all Convolution + InnerProduct layers)",
@@ -360,6 +382,7 @@ def main() -> None:
         ach_b = b["flops"] / (b["conv_ms"] / 1e3) / 1e12
         line["bf16"] = {"value": total_images / (b["ms"] / 1e3), "unit": "images/s", "ms_per_step": b["ms"] / args.steps,
                         "e2e_value": total_images / (b["ms_e2e"] / 1e3),
+                        "e2e_serial_value": total_images / (b["ms_e2e_serial"] / 1e3),
                         "roofline": {"achieved": ach_b, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach_b / pk["tflops"]},
                         "note": "plain bf16 conv path: fails the 1e-3 parity gate (bf16 rounding of activations), "
                                 "reported as BASELINE.json config 3 asks; proposals/image differ accordingly",

@@ -116,6 +116,17 @@ MSCNN_API int mscnn_pack_fc_weights(const float* w_f32, void* w_hi, void* w_lo, 
 MSCNN_API int mscnn_conv3x3_c3_forward(const float* x, const float* w, const float* bias, void* y_hi, void* y_lo,
                              int N, int H, int W, int Cout, int Cout_pad, int relu, void* stream);
 
+/* conv1_1 as one tensor-core kernel (mscnn_b200/csrc/conv_c3_tc.cu): 3 -> 64 channels, 3x3, pad 1, straight
+ * from the fp32 NCHW input blob to NHWC bf16 planes [N][H][W][64] (+ReLU).  Same reference call sites as
+ * mscnn_conv_forward (conv_layer.cpp:25-40, relu_layer.cpp:9-19).  The horizontal taps are overlapping views
+ * of one staged pixel row, expressed in the UMMA shared-memory descriptor (no im2col tensor, no padded copy).
+ * packed_w: mscnn_conv1_tc_packed_bytes() bytes filled by mscnn_pack_conv1_tc_weights from fp32 [64][3][3][3];
+ * y_lo == NULL selects the plain bf16 path (pack with split = 0 or 1, the lo plane is simply unused). */
+MSCNN_API int mscnn_conv1_tc_packed_bytes(void);
+MSCNN_API int mscnn_pack_conv1_tc_weights(const float* w_f32, void* packed, int split, void* stream);
+MSCNN_API int mscnn_conv1_tc_forward(const float* x, const void* packed_w, const float* bias64, void* y_hi,
+                                     void* y_lo, int N, int H, int W, int relu, void* stream);
+
 /* Narrow-output k x k heads (LFCN_*: Cout = 9, k = 5 / 7).  A direct k x k conv with tiny Cout
  * wastes the tensor core (N = 16..32) and re-reads the activation tile once per tap.  Instead the
  * horizontal taps move into the GEMM's N dimension and only the vertical taps stay in K:
@@ -380,6 +391,10 @@ MSCNN_API int mscnn_net_reshape_blob(void* net, const char* blob, int n, int c, 
 MSCNN_API int mscnn_net_reshape(void* net);
 MSCNN_API int mscnn_net_set_blob(void* net, const char* blob, const float* host, long count);       /* async H2D */
 MSCNN_API int mscnn_net_set_blob_device(void* net, const char* blob, const float* dev, long count); /* async D2D */
+/* Upload for the NEXT forward while the current one still runs: H2D on a private copy stream that waits (on the
+ * device) until the layers reading `blob` in the forward in flight have run; the next mscnn_net_forward waits
+ * for the copy.  `host` should be pinned and must stay valid until that forward has been issued. */
+MSCNN_API int mscnn_net_set_blob_async(void* net, const char* blob, const float* host, long count);
 MSCNN_API int mscnn_net_get_blob(void* net, const char* blob, float* host, long count);             /* D2H + sync */
 MSCNN_API const float* mscnn_net_blob_device(void* net, const char* blob);
 /* uint8 host images -> pre-processing kernels -> the input blob (N, in size and out size from the plan / blob). */

@@ -165,6 +165,13 @@ def _declare(L: C.CDLL) -> None:
     L.mscnn_kitti_evaluate.argtypes = [C.c_char_p] * 3 + [c_void_p]
 
 
+    L.mscnn_conv1_tc_packed_bytes.restype = c_int
+    L.mscnn_pack_conv1_tc_weights.restype = c_int
+    L.mscnn_pack_conv1_tc_weights.argtypes = [c_void_p, c_void_p, c_int, c_void_p]
+    L.mscnn_conv1_tc_forward.restype = c_int
+    L.mscnn_conv1_tc_forward.argtypes = [c_void_p] * 5 + [c_int] * 4 + [c_void_p]
+
+
 def check(rc: int, what: str = "") -> None:
     if rc != OK:
         raise MscnnError(f"{what or 'mscnn call'} failed with status {rc}")

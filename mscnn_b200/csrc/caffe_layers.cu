@@ -206,13 +206,42 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
   // conv1_1-style layer (3 input channels, 3x3, pad 1): K = 27 is far below one 64-channel
   // tensor-core k-block; it runs as a direct exact-fp32 kernel straight from the NCHW input blob.
   const bool first_path = (channels_ == 3 && kernel_h_ == 3 && kernel_w_ == 3 && pad_h_ == 1 && pad_w_ == 1);
-  const char* conv1_mode = std::getenv("MSCNN_CONV1");  // "direct" | "patch" | default = pixel-pair GEMM
-  if (first_path && (W % 2 == 0) && num_output_ % 64 == 0 && !conv1_mode) {
+  const char* conv1_mode = std::getenv("MSCNN_CONV1");  // "pair" | "direct" | "patch" | default = single tensor-core kernel
+  if (first_path && num_output_ == 64 && !conv1_mode) {
+    // One kernel from the fp32 NCHW blob to planes: pixel rows staged once, the horizontal taps are
+    // descriptor-shifted views of them (mscnn_conv1_tc_forward, conv_c3_tc.cu).
+    Blob<Dtype>* wb = this->blobs_[0].get();
+    constexpr long kTcKey = -64;
+    if (packed_.w_version != wb->version() || packed_.key != kTcKey) {
+      packed_.w.reserve((size_t)mscnn_conv1_tc_packed_bytes(), false);
+      MSCNN_CHECK(mscnn_pack_conv1_tc_weights(wb->gpu_data(), packed_.w.hi, 1, Caffe::stream()));
+      packed_.w_version = wb->version();
+      packed_.key = kTcKey;
+      packed_.b_version = ~0ul;
+      if (packed_.bias) { CUDA_CHECK(cudaFree(packed_.bias)); packed_.bias = nullptr; }
+    }
+    const unsigned long bver = bias ? bias->version() : 0;
+    if (!packed_.bias || packed_.b_version != bver) {
+      if (!packed_.bias) CUDA_CHECK(cudaMalloc(&packed_.bias, sizeof(float) * 64));
+      CUDA_CHECK(cudaMemsetAsync(packed_.bias, 0, sizeof(float) * 64, Caffe::stream()));
+      if (bias)
+        CUDA_CHECK(cudaMemcpyAsync(packed_.bias, bias->gpu_data(), sizeof(float) * 64, cudaMemcpyDeviceToDevice,
+                                   Caffe::stream()));
+      packed_.b_version = bver;
+    }
+    packed_.cout_pad = 64;
+    typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
+    MSCNN_CHECK(mscnn_conv1_tc_forward(bottom[0]->gpu_data(), packed_.w.hi, packed_.bias, y.hi, split ? y.lo : nullptr,
+                                       N, H, W, fuse_relu_ ? 1 : 0, Caffe::stream()));
+    return;
+  }
+  if (first_path && (W % 2 == 0) && num_output_ % 64 == 0 && conv1_mode && std::string(conv1_mode) == "pair") {
     // Pixel-pair GEMM: rows = two adjacent pixels (K = 54 of 64), block-diagonal weights, the output
     // [N][H][W/2][2*Cout] is the NHWC tensor [N][H][W][Cout] (see mscnn_im2col3x3_c3_pair_to_planes).
     const int cp = num_output_;  // multiple of 64
     Blob<Dtype>* wb = this->blobs_[0].get();
-    if (packed_.w_version != wb->version() || packed_.split != split || packed_.cout_pad != 2 * cp) {
+    if (packed_.w_version != wb->version() || packed_.split != split || packed_.cout_pad != 2 * cp || packed_.key != -2) {
+      packed_.key = -2;
       packed_.w.reserve((size_t)2 * cp * 64 * 2, split);
       MSCNN_CHECK(mscnn_pack_conv1_pair_weights(wb->gpu_data(), packed_.w.hi, split ? packed_.w.lo : nullptr,
                                                 num_output_, cp, Caffe::stream()));

@@ -2,6 +2,7 @@
 // gateway matlab/+caffe/private/caffe_.cpp and pycaffe's _caffe.cpp play in the reference).
 // Lookup failures return MSCNN_ERR_INVALID; structural errors abort like Caffe (LOG(FATAL)).
 #include <cstring>
+#include <algorithm>
 #include <sstream>
 #include <string>
 
@@ -19,8 +20,17 @@ struct NetHandle {
   caffe::BoxOutputLayer<float>* box = nullptr;
   void* det_ws = nullptr;
   size_t det_ws_bytes = 0;
+  // asynchronous input upload (mscnn_net_set_blob_async): a copy stream plus two events order the H2D copy
+  // of the NEXT forward's input against the layers of the CURRENT forward that still read the blob.
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t input_ready = nullptr, inputs_consumed = nullptr;
+  bool pending_input = false, consumed_valid = false;
+  int pending_consumer = -1;
   ~NetHandle() {
     if (det_ws) cudaFree(det_ws);
+    if (input_ready) cudaEventDestroy(input_ready);
+    if (inputs_consumed) cudaEventDestroy(inputs_consumed);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 };
 NetHandle* H(void* h) { return static_cast<NetHandle*>(h); }
@@ -213,10 +223,70 @@ const float* mscnn_net_blob_device(void* h, const char* name) {
 
 // layers [from, to] inclusive; to < 0 = last (Net::ForwardFromTo, net.cpp:544-555)
 int mscnn_net_forward(void* h, int from, int to) {
-  Net<float>* net = H(h)->net.get();
+  NetHandle* nh = H(h);
+  Net<float>* net = nh->net.get();
   if (to < 0) to = (int)net->layers().size() - 1;
   if (from < 0 || from > to || to >= (int)net->layers().size()) return MSCNN_ERR_INVALID;
+  if (nh->pending_input) {
+    // the upload issued by mscnn_net_set_blob_async must land before the first layer runs; once the last
+    // layer that reads the blob has been queued, the next upload may overwrite it
+    if (cudaStreamWaitEvent(Caffe::stream(), nh->input_ready, 0) != cudaSuccess) return MSCNN_ERR_CUDA;
+    nh->pending_input = false;
+    const int c = nh->pending_consumer;
+    if (c >= from && c < to) {
+      net->ForwardFromTo(from, c);
+      if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess) return MSCNN_ERR_CUDA;
+      nh->consumed_valid = true;
+      net->ForwardFromTo(c + 1, to);
+      return MSCNN_OK;
+    }
+    net->ForwardFromTo(from, to);
+    if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess) return MSCNN_ERR_CUDA;
+    nh->consumed_valid = true;
+    return MSCNN_OK;
+  }
   net->ForwardFromTo(from, to);
+  return MSCNN_OK;
+}
+// host -> blob on a separate copy stream: returns immediately; the copy starts as soon as the layers of the
+// forward in flight that read this blob have run, and the next mscnn_net_forward waits for it on the device.
+// `host` must stay valid (and should be pinned) until that forward has been issued.
+int mscnn_net_set_blob_async(void* h, const char* name, const float* host, long count) {
+  NetHandle* nh = H(h);
+  Net<float>* net = nh->net.get();
+  if (!net->has_blob(name)) return MSCNN_ERR_INVALID;
+  Blob<float>* b = net->blob_by_name(name).get();
+  if (b->count() != count) return MSCNN_ERR_INVALID;
+  if (!nh->copy_stream) {
+    if (cudaStreamCreateWithFlags(&nh->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&nh->input_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&nh->inputs_consumed, cudaEventDisableTiming) != cudaSuccess)
+      return MSCNN_ERR_CUDA;
+  }
+  // last layer that reads the blob, looking through Split layers (their tops share the blob's storage)
+  int consumer = -1;
+  const std::vector<std::vector<Blob<float>*> >& bv = net->bottom_vecs();
+  const std::vector<std::vector<Blob<float>*> >& tv = net->top_vecs();
+  std::vector<Blob<float>*> aliases(1, b);
+  for (size_t i = 0; i < bv.size(); ++i)
+    for (Blob<float>* q : bv[i])
+      if (std::find(aliases.begin(), aliases.end(), q) != aliases.end()) {
+        consumer = (int)i;
+        if (std::string(net->layers()[i]->type()) == "Split") aliases.insert(aliases.end(), tv[i].begin(), tv[i].end());
+      }
+  float* dst = b->mutable_gpu_data();
+  if (nh->consumed_valid && cudaStreamWaitEvent(nh->copy_stream, nh->inputs_consumed, 0) != cudaSuccess) return MSCNN_ERR_CUDA;
+  if (!nh->consumed_valid) {
+    // no forward has recorded a consumption point yet: order after everything queued on the net stream
+    if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess ||
+        cudaStreamWaitEvent(nh->copy_stream, nh->inputs_consumed, 0) != cudaSuccess)
+      return MSCNN_ERR_CUDA;
+  }
+  if (cudaMemcpyAsync(dst, host, sizeof(float) * count, cudaMemcpyHostToDevice, nh->copy_stream) != cudaSuccess ||
+      cudaEventRecord(nh->input_ready, nh->copy_stream) != cudaSuccess)
+    return MSCNN_ERR_CUDA;
+  nh->pending_input = true;
+  nh->pending_consumer = consumer;
   return MSCNN_OK;
 }
 int mscnn_net_set_layer_timing(void* h, int on) {

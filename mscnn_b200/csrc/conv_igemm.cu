@@ -50,6 +50,8 @@ struct IgemmParams {
   int store_full;     // also store the un-pooled tile (0 when only the pooling layer reads it)
   int stages, epi_bufs;
   int fat;            // split mode with all four operand tiles (A_hi, A_lo, B_hi, B_lo) in one stage
+  int wide;           // fat mode, two MMAs per K step: A_hi x [B_hi | B_lo] (N = 2 BLOCK_N, two accumulators
+                      // side by side) and A_lo x B_hi; the epilogue adds the two accumulators
   int mt;             // M sub-tiles (128 pixels each) per CTA tile: one weight tile feeds mt activation tiles
   int tmem_cols;      // 2 * mt * BLOCK_N rounded to a power of two >= 32
   const float* bias;  // [Cout_pad]
@@ -78,6 +80,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   const __grid_constant__ CUtensorMap tmP_lo, const IgemmParams p) {
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr uint32_t kIdesc = ptx::umma_idesc_bf16(kBlockM, BLOCK_N);
+  constexpr uint32_t kIdescWide = ptx::umma_idesc_bf16(kBlockM, BLOCK_N <= 128 ? 2 * BLOCK_N : BLOCK_N);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -218,7 +221,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * MT * BLOCK_N);
+      const uint32_t acc_w = static_cast<uint32_t>(p.wide ? 2 * BLOCK_N : BLOCK_N);  // TMEM columns per sub-tile
+      const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * MT) * acc_w;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(full_bar(stage), phase);
         ptx::tc_fence_after();
@@ -228,9 +232,20 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 #pragma unroll
           for (int j = 0; j < kMaxMt; ++j) {
             if (j < MT) {
-              const uint32_t d_tmem = d_base + static_cast<uint32_t>(j * BLOCK_N);
+              const uint32_t d_tmem = d_base + static_cast<uint32_t>(j) * acc_w;
               const uint64_t a_desc = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub);
-              if (p.fat) {
+              if (p.wide) {
+                // B_hi and B_lo are adjacent in the stage = one K-major tile of 2 BLOCK_N rows: A_hi meets both
+                // in ONE MMA (columns [0, BN) = hi*hi, [BN, 2 BN) = hi*lo), then A_lo * B_hi adds to the first
+                // half.  Per K step the tensor core reads 2 A tiles + 3 B tiles from shared memory instead of
+                // 3 + 3: narrow-N layers are bound by exactly that read bandwidth (128 B/clk/SM).
+                const uint64_t a_lo = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub + kABytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  ptx::umma_bf16(d_tmem, a_desc + 2u * k, b_desc + 2u * k, kIdescWide, (kb | k) != 0 ? 1u : 0u);
+                  ptx::umma_bf16(d_tmem, a_lo + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                }
+              } else if (p.fat) {
                 // three products per K step from one stage: hi*lo, lo*hi, hi*hi
                 const uint64_t a_lo = ptx::umma_desc_sw128(sA + stage * a_stride + j * a_sub + kABytes);
 #pragma unroll
@@ -281,7 +296,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       for (int sub = 0; sub < MT; ++sub) {
         int tw, th, tn;
         m_coords(m0 + sub, tw, th, tn);
-        const uint32_t t_row = tmem_base + static_cast<uint32_t>((acc * MT + sub) * BLOCK_N) +
+        const uint32_t t_row = tmem_base + static_cast<uint32_t>((acc * MT + sub) * (p.wide ? 2 * BLOCK_N : BLOCK_N)) +
                                (static_cast<uint32_t>(quarter * 32) << 16);
 
         if (p.out_mode == MSCNN_OUT_NHWC_BF16) {
@@ -291,6 +306,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
               uint32_t v[64];
               ptx::tmem_ld_32x32(t_row + chunk * 64, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
               ptx::tmem_ld_32x32(t_row + chunk * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+              uint32_t u[64];
+              if (p.wide) {
+                ptx::tmem_ld_32x32(t_row + BLOCK_N + chunk * 64, *reinterpret_cast<uint32_t(*)[32]>(&u[0]));
+                ptx::tmem_ld_32x32(t_row + BLOCK_N + chunk * 64 + 32, *reinterpret_cast<uint32_t(*)[32]>(&u[32]));
+              }
               // the staging buffer we are about to overwrite must have been read by its TMA store
               if (issuer) {
                 if (p.epi_bufs == 1) ptx::tma_store_wait_read<0>();
@@ -298,6 +318,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
               }
               ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // also publishes bias_s
               ptx::tmem_ld_wait();
+              if (p.wide) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+              }
               const uint32_t buf = sEpi + ebuf * epi_buf_bytes;
               const uint32_t row_hi = buf + row * 128;
               const uint32_t row_lo = row_hi + kABytes;
@@ -420,6 +444,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
           for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(t_row + chunk * 32, v);
+            if (p.wide) {
+              uint32_t u[32];
+              ptx::tmem_ld_32x32(t_row + BLOCK_N + chunk * 32, u);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(u[i]));
+            }
             ptx::tmem_ld_wait();
             if (p.out_mode == MSCNN_OUT_NHWC_F32) {
               if (ok) {
@@ -569,6 +600,8 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   // narrow-N layers of the fp32-faithful path: A_hi / B_hi are fetched once instead of twice and a
   // barrier round trip covers 3x the MMAs (conv1_2: 6.3 -> 3.9 ms, profiles/r01_probe_layers*.log).
   p.fat = (split && BN <= 128 && !getenv("MSCNN_NO_FAT")) ? 1 : 0;
+  p.wide = (p.fat && !getenv("MSCNN_NO_WIDE")) ? 1 : 0;
+  const int acc_mul = p.wide ? 2 : 1;  // accumulator columns per sub-tile = acc_mul * BN
   // M sub-tiles per CTA tile: for narrow N one weight tile should feed several activation tiles
   // (fewer hot-line weight fetches and barrier round trips per MMA).  2 * mt * BN TMEM columns <= 512.
   const int m_tiles_total = p.tiles_w * p.tiles_h * p.tiles_n;
@@ -578,7 +611,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (const char* e = getenv("MSCNN_MT")) mt = atoi(e);
   if (mt > kMaxMt) mt = kMaxMt;
   if (mt < 1) mt = 1;
-  while (mt > 1 && (2 * mt * BN > 512 || m_tiles_total % mt != 0 || m_tiles_total / mt * p.n_tiles < mscnn_sm_count())) mt >>= 1;
+  while (mt > 1 && (2 * mt * BN * acc_mul > 512 || m_tiles_total % mt != 0 || m_tiles_total / mt * p.n_tiles < mscnn_sm_count())) mt >>= 1;
   const int epi_unit = (d->out_mode == MSCNN_OUT_NHWC_BF16) ? (kABytes + (pool ? kABytes / 4 : 0)) * (p.has_lo_out ? 2 : 1) : 0;
   const int misc = BN * 4 + 8 * (2 * 8 + 4) + 16 + 1024 /*alignment slack*/;
   const int budget = 227 * 1024;
@@ -598,14 +631,14 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (stages < 2) return MSCNN_ERR_INVALID;
   p.mt = mt;
   int tcols = 32;
-  while (tcols < 2 * mt * BN) tcols <<= 1;
+  while (tcols < 2 * mt * BN * acc_mul) tcols <<= 1;
   p.tmem_cols = tcols;
   p.stages = stages;
   p.epi_bufs = epi_bufs;  // 0 in fp32-output mode: no staging region is carved
   const size_t smem = (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
   if (getenv("MSCNN_VERBOSE_CONV"))
-    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
-            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.num_terms, stages,
+    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
+            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.num_terms, stages,
             epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
   CUtensorMap maps[8];

@@ -43,6 +43,7 @@ def _declare(L):
     L.mscnn_net_reshape_blob.argtypes = [C.c_void_p, C.c_char_p] + [C.c_int] * 4
     L.mscnn_net_set_blob.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
     L.mscnn_net_set_input_images.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.mscnn_net_set_blob_async.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
     L.mscnn_net_set_blob_device.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
     L.mscnn_net_get_blob.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_long]
     L.mscnn_net_blob_device.restype = C.c_void_p
@@ -186,6 +187,15 @@ class Net:
         return p
 
     # ---- execution -----------------------------------------------------------------------
+    def set_input_async(self, name: str, data) -> None:
+        """Pinned host tensor / numpy array -> input blob on the copy stream, for the NEXT forward: the copy
+        overlaps the rest of the forward in flight (it starts once the layers reading `name` have run)."""
+        if self.blob_shape(name) != tuple(data.shape):
+            raise capi.MscnnError("set_input_async does not reshape: call set_input once with this shape first")
+        n = data.numel() if hasattr(data, "numel") else data.size
+        assert str(data.dtype) in ("torch.float32", "float32")
+        capi.check(self._L.mscnn_net_set_blob_async(self._h, name.encode(), capi.ptr(data), n), "set_blob_async")
+
     def set_input_images(self, name: str, pre, images) -> None:
         """uint8 host images [N][h][w][3] (numpy or pinned CPU tensor) -> device pre-processing (`pre` = an
         ops.Preprocess plan) -> the input blob; the MATLAB code before net.forward, run_mscnn_detection.m:64-69."""

@@ -323,6 +323,21 @@ def conv3x3_c3_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None,
     return Planes(y_hi, y_lo, cout)
 
 
+def conv1_tc_forward(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor | None, relu: bool, split: bool) -> Planes:
+    """conv1_1 (3 -> 64, 3x3, pad 1) as the single tensor-core kernel: x [N,3,H,W] fp32 NCHW -> planes."""
+    n, c, h, wd = x.shape
+    assert c == 3 and tuple(w.shape) == (64, 3, 3, 3) and x.is_contiguous() and w.is_contiguous()
+    L = capi.lib()
+    packed = torch.empty(L.mscnn_conv1_tc_packed_bytes(), dtype=torch.uint8, device=x.device)
+    capi.check(L.mscnn_pack_conv1_tc_weights(capi.ptr(w), capi.ptr(packed), int(split), _stream()), "pack_conv1_tc")
+    bias = b if b is not None else torch.zeros(64, device=x.device)
+    y_hi = torch.empty((n, h, wd, 64), dtype=torch.bfloat16, device=x.device)
+    y_lo = torch.empty_like(y_hi) if split else None
+    capi.check(L.mscnn_conv1_tc_forward(capi.ptr(x), capi.ptr(packed), capi.ptr(bias), capi.ptr(y_hi), capi.ptr(y_lo),
+                                        n, h, wd, int(relu), _stream()), "conv1_tc_forward")
+    return Planes(y_hi, y_lo, 64)
+
+
 # ---- pre-processing (SURVEY.md 8(f)-3) ------------------------------------------------------------
 def imresize_contributions(in_len: int, out_len: int) -> tuple[np.ndarray, np.ndarray]:
     """The library's imresize tap tables for one dimension (host-only call, works without a GPU)."""

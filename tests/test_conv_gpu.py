@@ -183,6 +183,33 @@ def test_conv1_1_direct(cuda, split):
 
 
 @pytest.mark.parametrize("split", [True, False], ids=["split", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 21, 150), (1, 5, 40), (3, 40, 384), (1, 3, 129), (2, 160, 640)])
+def test_conv1_1_tensor_core(cuda, split, shape):
+    """conv1_1 as the single tensor-core kernel (descriptor-shifted pixel rows; the path the Net uses).
+    Widths below / across / at multiples of the 128-pixel tile, more tiles than SMs in the last case."""
+    from mscnn_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(4)
+    n, h, w = shape
+    x = (torch.randint(0, 256, (n, 3, h, w), generator=g).float()
+         - torch.tensor([104.0, 117.0, 123.0]).view(1, 3, 1, 1)).to(cuda).contiguous()
+    x[0, :, h // 2, w // 3] += 0.37          # not bf16-representable: exercises the lo plane of the input
+    wt = (torch.randn((64, 3, 3, 3), generator=g) * (2.0 / 27) ** 0.5 / 64).to(cuda)
+    b = (torch.randn((64,), generator=g) * 0.1).to(cuda)
+    for relu in (True, False):
+        yp = ops.conv1_tc_forward(x, wt, b, relu=relu, split=split)
+        got = ops.planes_to_nchw(yp)
+        torch.cuda.synchronize()
+        if split:
+            ref = _ref_conv(x, wt, b, 1, relu)
+            rms = float(ref.pow(2).mean().sqrt())
+            _report("conv1_1_tc", got, ref, 2e-5, 2e-5 * rms)
+        else:
+            ref = _ref_conv(x.bfloat16().float(), wt.bfloat16().float(), b, 1, relu)
+            rms = float(ref.pow(2).mean().sqrt())
+            _report("conv1_1_tc", got, ref, 2.0 ** -8, 1e-5 * rms)
+
+
+@pytest.mark.parametrize("split", [True, False], ids=["split", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 64, 64, 192, 64), (1, 64, 128, 320, 128), (2, 128, 24, 80, 256), (3, 64, 10, 12, 64)])
 def test_conv_fused_pool(cuda, split, shape):
     """mscnn_conv_forward with pool_hi set == conv followed by mscnn_pool_forward, bit for bit; the

@@ -367,3 +367,28 @@ def test_cascade_final_detections_vs_oracle(cuda):
             assert cnt[i] == len(ref), (kind, i)
             assert np.array_equal(dets[i, : cnt[i]], ref), (kind, i)
             start += n_i
+
+
+def test_async_input_upload_pipelines_correctly(cuda):
+    """mscnn_net_set_blob_async: the upload for the NEXT forward is issued while the current forward is still
+    running; every forward must see exactly the batch uploaded for it (two alternating batches, several rounds),
+    and the outputs must equal those of the synchronous set_input path bit for bit."""
+    import torch
+    from mscnn_b200 import models, net as mnet, synth
+    mnet.set_precision("fp32")
+    h, w = 96, 320
+    net = mnet.Net(models.kitti(h, w, 7, False, batch=2))
+    net.set_params(synth.make_weights(net.layers()))
+    batches = [torch.from_numpy(synth.make_images(2, h, w, first_index=i * 2)).pin_memory() for i in range(2)]
+    want = []
+    for b in batches:
+        out = net.forward(data=b.numpy())
+        want.append({k: v.copy() for k, v in out.items()})
+    assert not np.array_equal(want[0]["cls_pred"], want[1]["cls_pred"])
+    net.set_input_async("data", batches[0])
+    for step in range(6):
+        net.forward_only()
+        net.set_input_async("data", batches[(step + 1) % 2])     # while this forward's ROI head is still queued
+        got = {o: net.blob(o) for o in net.outputs}
+        for k in got:
+            assert np.array_equal(got[k], want[step % 2][k]), (step, k)
