@@ -241,6 +241,9 @@ conv_c3_tc_kernel(const __grid_constant__ CUtensorMap tmO_hi, const __grid_const
     const bool issuer = (et == 0);
     int acc = 0, ebuf = 0;
     uint32_t acc_phase = 0;
+    float bias_r[32];  // this thread's 32 output channels: constant over tiles
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias_r[i] = bias_s[half * 32 + i];
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int tw = tile % p.tiles_w;
       const int y = (tile / p.tiles_w) % p.H;
@@ -259,17 +262,18 @@ conv_c3_tc_kernel(const __grid_constant__ CUtensorMap tmO_hi, const __grid_const
         uint32_t hi[4], lo[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float f0 = __uint_as_float(v[j * 8 + 2 * q]) + bias_s[half * 32 + j * 8 + 2 * q];
-          float f1 = __uint_as_float(v[j * 8 + 2 * q + 1]) + bias_s[half * 32 + j * 8 + 2 * q + 1];
+          float f0 = __uint_as_float(v[j * 8 + 2 * q]) + bias_r[j * 8 + 2 * q];
+          float f1 = __uint_as_float(v[j * 8 + 2 * q + 1]) + bias_r[j * 8 + 2 * q + 1];
           if (p.relu) {
             f0 = fmaxf(f0, 0.f);
             f1 = fmaxf(f1, 0.f);
           }
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
-          hi[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-          const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
-          const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
-          lo[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) | (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+          // packed conversions (cvt.rn.bf16x2.f32): same rounding as two scalar ones, half the F2F issue slots
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+          hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+          const __nv_bfloat162 l2 = __floats2bfloat162_rn(f0 - __uint_as_float(hi[q] << 16),
+                                                          f1 - __uint_as_float(hi[q] & 0xFFFF0000u));
+          lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
         }
         const uint32_t off = static_cast<uint32_t>(((half * 4 + j) ^ (row & 7)) << 4);  // 128B swizzle
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),

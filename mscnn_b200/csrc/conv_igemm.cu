@@ -52,6 +52,10 @@ struct IgemmParams {
   int fat;            // split mode with all four operand tiles (A_hi, A_lo, B_hi, B_lo) in one stage
   int wide;           // fat mode, two MMAs per K step: A_hi x [B_hi | B_lo] (N = 2 BLOCK_N, two accumulators
                       // side by side) and A_lo x B_hi; the epilogue adds the two accumulators
+  int rowshare;       // wide mode, 3 horizontal taps, 128x1 pixel boxes: ONE activation tile of (128 + 2) pixels per
+                      // (dy, channel chunk) serves the three dx taps through descriptor row shifts; activation and
+                      // weight tiles travel in separate rings (sa_slots x a_slot bytes, sb_slots x 2 weight tiles)
+  int sa_slots, sb_slots, a_slot;
   int mt;             // M sub-tiles (128 pixels each) per CTA tile: one weight tile feeds mt activation tiles
   int tmem_cols;      // 2 * mt * BLOCK_N rounded to a power of two >= 32
   const float* bias;  // [Cout_pad]
@@ -86,14 +90,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
 
-  const int S = p.stages;
+  const int S = p.stages;  // row-share mode: stages = sa_slots + sb_slots, barriers [0, sa_slots) = A ring, rest = B ring
   const int MT = p.mt;
   const uint32_t a_sub = p.fat ? 2u * kABytes : kABytes;     // one sub-tile: [A_hi] or [A_hi][A_lo]
   const uint32_t a_stride = a_sub * MT;                      // one stage: MT sub-tiles
   const uint32_t b_stride = p.fat ? 2u * kBBytes : kBBytes;  //            [B_hi] or [B_hi][B_lo]
   const uint32_t sA = smem_base;
-  const uint32_t sB = sA + S * a_stride;
-  const uint32_t sEpi = sB + S * b_stride;  // 1024-aligned: kABytes, kBBytes are multiples of 1024
+  const uint32_t sB = p.rowshare ? sA + p.sa_slots * p.a_slot : sA + S * a_stride;
+  const uint32_t sEpi = p.rowshare ? sB + p.sb_slots * 2u * kBBytes
+                                   : sB + S * b_stride;  // 1024-aligned: kABytes, kBBytes, a_slot are multiples of 1024
   constexpr int kPoolBytes = kABytes / 4;  // pooled tile: 32 rows x 128 B
   const int epi_buf_bytes = (kABytes + (p.pool ? kPoolBytes : 0)) * (p.has_lo_out ? 2 : 1);
   const uint32_t sMisc = sEpi + p.epi_bufs * epi_buf_bytes;
@@ -163,9 +168,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     // The whole warp walks the loops (warp-uniform control flow); one elected lane issues.
+    if (p.rowshare) {
+      // Row-share mode (MT == 1, 128x1 boxes): per (dy, channel chunk) one activation tile of 130 pixels, then the
+      // weight tiles [B_hi | B_lo] of the three dx taps; two independent rings.
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      const uint32_t a_tx = 2u * static_cast<uint32_t>(p.box_w + 2) * kBlockK * 2, b_tx = 2u * kBBytes;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int tw, th, tn;
+        m_coords(tile / p.n_tiles, tw, th, tn);
+        const int wa = tw * p.box_w - p.pad_w, ha = th - p.pad_h;
+        for (int dy = 0; dy < p.taps_h; ++dy) {
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+            ptx::mbar_wait(empty_bar(sa), pa ^ 1u);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(full_bar(sa), a_tx);
+              const uint32_t a0 = sA + sa * p.a_slot;
+              ptx::tma_load_4d(a0, &tmA_hi, full_bar(sa), cc * kBlockK, wa, ha + dy, tn);
+              ptx::tma_load_4d(a0 + p.a_slot / 2, &tmA_lo, full_bar(sa), cc * kBlockK, wa, ha + dy, tn);
+            }
+            __syncwarp();
+            if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
+            for (int dx = 0; dx < 3; ++dx) {
+              const int bi = p.sa_slots + sb;
+              ptx::mbar_wait(empty_bar(bi), pb ^ 1u);
+              if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(full_bar(bi), b_tx);
+                const uint32_t b0 = sB + sb * 2u * kBBytes;
+                const int kcol = ((dy * 3 + dx) * p.cin_chunks + cc) * kBlockK;
+                ptx::tma_load_2d(b0, &tmB_hi, full_bar(bi), kcol, n_tile * BLOCK_N);
+                ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
+              }
+              __syncwarp();
+              if (++sb == p.sb_slots) { sb = 0; pb ^= 1u; }
+            }
+          }
+        }
+      }
+    }
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles && !p.rowshare; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles, m0 = (tile / p.n_tiles) * MT;
       int w0[kMaxMt], h0[kMaxMt], n0[kMaxMt];
 #pragma unroll
@@ -218,7 +262,48 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    if (p.rowshare) {
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 2u * BLOCK_N;
+        uint32_t first = 0u;  // the first MMA of the tile overwrites the accumulator
+        for (int dy = 0; dy < p.taps_h; ++dy) {
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+            ptx::mbar_wait(full_bar(sa), pa);
+            const uint32_t a_hi = sA + sa * p.a_slot, a_lo = a_hi + p.a_slot / 2;
+            for (int dx = 0; dx < 3; ++dx) {
+              const int bi = p.sa_slots + sb;
+              ptx::mbar_wait(full_bar(bi), pb);
+              ptx::tc_fence_after();
+              if (ptx::elect_one()) {
+                // tap dx = the activation rows shifted by dx pixels: a K-major SWIZZLE_128B operand may start at any
+                // 128-byte row of a TMA-written tile (tools/umma_shift_probe.cu)
+                const uint64_t ah = ptx::umma_desc_sw128(a_hi + dx * 128), al = ptx::umma_desc_sw128(a_lo + dx * 128);
+                const uint64_t b_desc = ptx::umma_desc_sw128(sB + sb * 2u * kBBytes);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdescWide, (first | k) != 0 ? 1u : 0u);
+                  ptx::umma_bf16(d_tmem, al + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                }
+                ptx::umma_commit(empty_bar(bi));
+                if (dx == 2) ptx::umma_commit(empty_bar(sa));
+                if (dx == 2 && dy == p.taps_h - 1 && cc == p.cin_chunks - 1) ptx::umma_commit(tfull_bar(acc));
+              }
+              __syncwarp();
+              first = 1u;
+              if (++sb == p.sb_slots) { sb = 0; pb ^= 1u; }
+            }
+            if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
+          }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+    for (int tile = blockIdx.x; tile < total_tiles && !p.rowshare; tile += gridDim.x) {
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t acc_w = static_cast<uint32_t>(p.wide ? 2 * BLOCK_N : BLOCK_N);  // TMEM columns per sub-tile
@@ -337,13 +422,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                     f0 = fmaxf(f0, 0.f);
                     f1 = fmaxf(f1, 0.f);
                   }
-                  const __nv_bfloat16 h0 = __float2bfloat16_rn(f0), h1 = __float2bfloat16_rn(f1);
-                  hi[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-                          (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-                  const __nv_bfloat16 l0 = __float2bfloat16_rn(f0 - __bfloat162float(h0));
-                  const __nv_bfloat16 l1 = __float2bfloat16_rn(f1 - __bfloat162float(h1));
-                  lo[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-                          (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+                  // packed conversions (cvt.rn.bf16x2.f32): same rounding as scalar ones, half the issue slots
+                  const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                  hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+                  const __nv_bfloat162 l2 = __floats2bfloat162_rn(f0 - __uint_as_float(hi[q] << 16),
+                                                                  f1 - __uint_as_float(hi[q] & 0xFFFF0000u));
+                  lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
                 }
                 const uint32_t off = static_cast<uint32_t>((j ^ (row & 7)) << 4);  // 128B swizzle
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(row_hi + off),
@@ -390,13 +474,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   uint32_t oh[4], ol[4];
 #pragma unroll
                   for (int q = 0; q < 4; ++q) {
-                    const __nv_bfloat16 h0 = __float2bfloat16_rn(best[2 * q]), h1 = __float2bfloat16_rn(best[2 * q + 1]);
-                    oh[q] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-                            (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-                    const __nv_bfloat16 l0 = __float2bfloat16_rn(best[2 * q] - __bfloat162float(h0));
-                    const __nv_bfloat16 l1 = __float2bfloat16_rn(best[2 * q + 1] - __bfloat162float(h1));
-                    ol[q] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-                            (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(best[2 * q], best[2 * q + 1]);
+                    oh[q] = *reinterpret_cast<const uint32_t*>(&h2);
+                    const __nv_bfloat162 l2 = __floats2bfloat162_rn(best[2 * q] - __uint_as_float(oh[q] << 16),
+                                                                    best[2 * q + 1] - __uint_as_float(oh[q] & 0xFFFF0000u));
+                    ol[q] = *reinterpret_cast<const uint32_t*>(&l2);
                   }
                   const uint32_t pa = pbuf + pr * 128 + static_cast<uint32_t>((j ^ (pr & 7)) << 4);
                   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(pa), "r"(oh[0]), "r"(oh[1]),
@@ -629,21 +711,48 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   }
   if (stages > 8) stages = 8;
   if (stages < 2) return MSCNN_ERR_INVALID;
+  // Row-share mode: wide mode over 128 x 1 pixel boxes with three horizontal taps.  The activation tile of a
+  // (dy, channel chunk) is loaded ONCE with a one-pixel halo on each side (130 rows) and serves the three dx taps
+  // through descriptor row shifts; narrow-N layers are bound by shared-memory bandwidth (TMA fill + operand
+  // reads share 128 B/clk/SM, profiles/r01g_summary.md), and this removes two of three activation fills.
+  size_t smem_rs = 0;
+  if (p.wide && d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !getenv("MSCNN_NO_ROWSHARE")) {
+    const int a_plane = ((p.box_w + 2) * 128 + 1023) / 1024 * 1024;
+    const int a_slot = 2 * a_plane, b_slot = 2 * b_bytes;
+    for (int eb = (epi_unit == 0 ? 0 : 2); eb >= (epi_unit == 0 ? 0 : 1) && !p.rowshare; --eb) {
+      const int rings = budget - misc - eb * epi_unit;
+      for (int sa = 3; sa >= 2 && !p.rowshare; --sa) {
+        int sb = (rings - sa * a_slot) / b_slot;
+        if (sb > 5) sb = 5;
+        if (sb >= 3) {
+          p.rowshare = 1;
+          p.sa_slots = sa;
+          p.sb_slots = sb;
+          p.a_slot = a_slot;
+          epi_bufs = eb;
+          stages = sa + sb;
+          mt = 1;
+          smem_rs = (size_t)sa * a_slot + (size_t)sb * b_slot + (size_t)eb * epi_unit + misc;
+        }
+      }
+    }
+  }
   p.mt = mt;
   int tcols = 32;
   while (tcols < 2 * mt * BN * acc_mul) tcols <<= 1;
   p.tmem_cols = tcols;
   p.stages = stages;
   p.epi_bufs = epi_bufs;  // 0 in fp32-output mode: no staging region is carved
-  const size_t smem = (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
+  const size_t smem = p.rowshare ? smem_rs : (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
   if (getenv("MSCNN_VERBOSE_CONV"))
-    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
-            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.num_terms, stages,
+    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d rowshare=%d(%d+%d) terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
+            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.num_terms, stages,
             epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
   CUtensorMap maps[8];
   memset(maps, 0, sizeof(maps));
-  const uint32_t abox[4] = {64u, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
+  const uint32_t obox[4] = {64u, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
+  const uint32_t abox[4] = {64u, (uint32_t)(p.box_w + (p.rowshare ? 2 : 0)), (uint32_t)p.box_h, (uint32_t)p.box_n};
   const uint64_t adim[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
   int rc = tmap_nhwc_bf16(&maps[0], d->x_hi, adim, abox);
   if (rc) return rc;
@@ -665,13 +774,13 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (d->out_mode == MSCNN_OUT_NHWC_BF16) {
     const uint64_t odim[4] = {(uint64_t)d->Cout_pad, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)d->N};
     if (d->y_hi) {
-      rc = tmap_nhwc_bf16(&maps[4], d->y_hi, odim, abox);
+      rc = tmap_nhwc_bf16(&maps[4], d->y_hi, odim, obox);
       if (rc) return rc;
     } else {
       maps[4] = maps[0];
     }
     if (p.has_lo_out && d->y_lo) {
-      rc = tmap_nhwc_bf16(&maps[5], d->y_lo, odim, abox);
+      rc = tmap_nhwc_bf16(&maps[5], d->y_lo, odim, obox);
       if (rc) return rc;
     } else {
       maps[5] = maps[4];

@@ -108,6 +108,21 @@ __global__ void pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfl
 // Up to four pad_ratio variants of the same ROI set are pooled by the same warp (MS-CNN pools every
 // ROI twice, object and 1.5x context window, and concatenates): the context window contains the
 // object window, so the second variant mostly hits lines the first one just touched.
+// best[i] = max(best[i], hi[i] + lo[i]) for the 8 bf16 channels packed in `a` (+ `l` when has_lo)
+__device__ __forceinline__ void max8(Vec8& best, const uint4& a, const uint4& l, bool has_lo) {
+  const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, al[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v0 = __uint_as_float(ah[q] << 16), v1 = __uint_as_float(ah[q] & 0xFFFF0000u);
+    if (has_lo) {
+      v0 = v0 + __uint_as_float(al[q] << 16);
+      v1 = v1 + __uint_as_float(al[q] & 0xFFFF0000u);
+    }
+    best.v[2 * q] = fmaxf(best.v[2 * q], v0);
+    best.v[2 * q + 1] = fmaxf(best.v[2 * q + 1], v1);
+  }
+}
+
 struct RoiVariants {
   int count;
   float pad_ratio[4];
@@ -148,29 +163,63 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
       wstart = min(max(wstart + sw, 0), W);
       wend = min(max(wend + sw, 0), W);
       const bool empty = (hend <= hstart) || (wend <= wstart);
-      for (int g = lane; g < cg; g += 32) {
-        Vec8 best;
+      // 16-byte units, 32-bit indices (the feature map has < 2^31 / 8 elements: checked by the launcher).  The
+      // window is walked as one flattened pixel sequence, two pixels per step, and a lane owns channel groups g and
+      // g + 32 at once (C = 512: cg = 64), so up to eight 16-byte loads are in flight per lane: the kernel was
+      // bound by the latency of two (profiles/r01g_roi_pool.md).  fmaxf gives the reference's
+      // `if (x > max) max = x` result for every non-NaN input.
+      const uint4* xh4 = reinterpret_cast<const uint4*>(xh);
+      const uint4* xl4 = reinterpret_cast<const uint4*>(xl);
+      const bool has_lo = xl != nullptr;
+      const int bw = wend - wstart;
+      const int npx = empty ? 0 : (hend - hstart) * bw;
+      const int row_skip = (W - bw) * cg;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      for (int g = lane; g < cg; g += 64) {
+        const bool dual = g + 32 < cg;
+        Vec8 best0, best1;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) best.v[i] = empty ? 0.f : -3.402823466e+38f;
-        for (int h = hstart; h < hend; ++h) {
-          const size_t rowbase = ((size_t)(b * H + h) * W) * C + g * 8;
-          int w = wstart;
-          for (; w + 1 < wend; w += 2) {  // two independent loads in flight
-            const Vec8 v0 = load8(xh, xl, rowbase + (size_t)w * C);
-            const Vec8 v1 = load8(xh, xl, rowbase + (size_t)(w + 1) * C);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              best.v[i] = (v0.v[i] > best.v[i]) ? v0.v[i] : best.v[i];
-              best.v[i] = (v1.v[i] > best.v[i]) ? v1.v[i] : best.v[i];
+        for (int i = 0; i < 8; ++i) best0.v[i] = best1.v[i] = empty ? 0.f : -3.402823466e+38f;
+        int idx = ((b * H + hstart) * W + wstart) * cg + g;
+        int wpos = 0;
+        int k = 0;
+        for (; k + 1 < npx; k += 2) {
+          const int i0 = idx;
+          idx += cg;
+          if (++wpos == bw) { wpos = 0; idx += row_skip; }
+          const int i1 = idx;
+          idx += cg;
+          if (++wpos == bw) { wpos = 0; idx += row_skip; }
+          const uint4 a0 = __ldg(xh4 + i0), a1 = __ldg(xh4 + i1);
+          const uint4 c0 = dual ? __ldg(xh4 + i0 + 32) : z, c1 = dual ? __ldg(xh4 + i1 + 32) : z;
+          uint4 l0 = z, l1 = z, m0 = z, m1 = z;
+          if (has_lo) {
+            l0 = __ldg(xl4 + i0);
+            l1 = __ldg(xl4 + i1);
+            if (dual) {
+              m0 = __ldg(xl4 + i0 + 32);
+              m1 = __ldg(xl4 + i1 + 32);
             }
           }
-          if (w < wend) {
-            const Vec8 v0 = load8(xh, xl, rowbase + (size_t)w * C);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) best.v[i] = (v0.v[i] > best.v[i]) ? v0.v[i] : best.v[i];
+          max8(best0, a0, l0, has_lo);
+          max8(best0, a1, l1, has_lo);
+          if (dual) {
+            max8(best1, c0, m0, has_lo);
+            max8(best1, c1, m1, has_lo);
           }
         }
-        store8<true>(yh, yl, (size_t)bin * Ctot + var.c_off[vi] + g * 8, best);
+        if (k < npx) {
+          const uint4 a0 = __ldg(xh4 + idx);
+          const uint4 l0 = has_lo ? __ldg(xl4 + idx) : z;
+          max8(best0, a0, l0, has_lo);
+          if (dual) {
+            const uint4 c0 = __ldg(xh4 + idx + 32);
+            const uint4 m0 = has_lo ? __ldg(xl4 + idx + 32) : z;
+            max8(best1, c0, m0, has_lo);
+          }
+        }
+        store8<true>(yh, yl, (size_t)bin * Ctot + var.c_off[vi] + g * 8, best0);
+        if (dual) store8<true>(yh, yl, (size_t)bin * Ctot + var.c_off[vi] + (g + 32) * 8, best1);
       }
     }
   }
@@ -373,6 +422,7 @@ extern "C" int mscnn_roi_pool_multi_forward(const void* x_hi, const void* x_lo, 
     var.c_off[i] = out_channel_offsets[i];
   }
   if (R == 0) return MSCNN_OK;
+  if ((size_t)N * H * W * (C / 8) >= (size_t)1 << 31) return MSCNN_ERR_INVALID;  // 32-bit 16-byte indices in the kernel
   const size_t total = (size_t)R * pooled_h * pooled_w * 32;  // one warp per (ROI, bin)
   mscnn::note_launch();
   roi_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(

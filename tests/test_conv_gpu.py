@@ -53,6 +53,11 @@ CASES = [
     # enough M tiles that a CTA tile holds several 128-pixel sub-tiles (mt = 2 / 4 path)
     ("mt_n64",         2, 64, 128, 160, 64, 3, 1),
     ("mt_n128",        2, 64, 128, 320, 128, 3, 1),
+    # W a multiple of 128 with narrow N: 128x1 boxes -> row-share mode (one 130-pixel activation tile per dy,
+    # the dx taps are descriptor row shifts), one and two channel chunks, more tiles than ring slots
+    ("rowshare_n64",   1, 64, 6, 256, 64, 3, 1),
+    ("rowshare_n128",  2, 128, 5, 384, 128, 3, 1),
+    ("rowshare_many",  2, 64, 40, 512, 64, 3, 1),
 ]
 
 
