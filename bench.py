@@ -359,12 +359,13 @@ def main() -> None:
                        "strictly in order on one stream"},
         # counted by the library itself (mscnn_kernel_launch_count) inside the timed resident region, all ranks
         "gpu_launches": r["launched"],
-        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel<BLOCK_N> (all Convolution + InnerProduct layers)",
+        "roofline": {"bound": "tensor", "kernel": "conv_igemm_kernel<BLOCK_N> + conv_c3_tc_kernel (all Convolution + InnerProduct layers)",
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                     # dram__bytes_read+write of ONE representative launch of this kernel from the committed
-                     # `ncu --set full` capture (conv3_2, BLOCK_N=256: 1.015 GB + 0.966 GB, equal to its
-                     # algorithmic 2.01 GB of planes in + out; profiles/r01b_summary.md)
-                     "traffic": 1.981e9, "traffic_launch": "conv3_2 (profiles/r01b_conv3_2_split_N256.ncu-rep)",
+                     # mean dram__bytes_read + dram__bytes_write per launch of the convolution kernels
+                     # (conv_igemm_kernel<*> + conv_c3_tc_kernel, 378 launches = 14 forwards) from the committed ncu
+                     # launch list profiles/r01h_launches.csv; per-layer `ncu --set full` captures (conv3_2: 1.02 GB +
+                     # 0.97 GB = its algorithmic 2.01 GB of planes in + out) in profiles/r01h_summary.md
+                     "traffic": 1.342e9, "traffic_source": "profiles/r01h_launches.csv (mean over the step's conv launches)",
                      "algorithmic_gflop_per_step": r["flops"] / 1e9,
                      "launches_per_step": r["conv_launches"],
                      "avg_launch_ms": r["conv_ms"] / r["conv_launches"],

@@ -6,7 +6,7 @@
 // must read 12 B and write 64 channels x 2 B (x2 for the (hi, lo) pair) = 256 B.  The previous formulation
 // (im2col3x3_c3_pair_kernel + the generic implicit-GEMM kernel) wrote and re-read a 2 GB patch tensor and ran
 // the generic epilogue with one staging buffer: 2.7 ms for 8 x 768 x 2560 pixels against a 0.65 ms HBM floor
-// (profiles/r01e_conv1_1_summary.md).  Here:
+// (profiles/r01h_summary.md).  Here:
 //   * producer warps read the fp32 image rows themselves (coalesced along x, zero padding by predication),
 //     split to bf16 (hi, lo) and write them to shared memory as PIXEL ROWS of 8 channels (3 real) = 16 B per
 //     pixel.  Nothing else is staged: no im2col tensor, no padded copy of the image.

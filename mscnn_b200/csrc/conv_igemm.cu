@@ -56,6 +56,11 @@ struct IgemmParams {
                       // (dy, channel chunk) serves the three dx taps through descriptor row shifts; activation and
                       // weight tiles travel in separate rings (sa_slots x a_slot bytes, sb_slots x 2 weight tiles)
   int sa_slots, sb_slots, a_slot;
+  int acc_sets;       // TMEM accumulator sets: 2 (epilogue of tile i overlaps the MMAs of tile i + 1) or, when two wide
+                      // sub-tiles of BLOCK_N = 128 already fill the 512 columns, 1 (vpool mode only)
+  int vpool;          // row-share mode over image-row PAIRS (mt = 2: sub-tile j = row 2 th + j) with the 2x2 MAX pooling
+                      // done in registers by the epilogue (vertical max of the two accumulators, horizontal max by
+                      // lane shuffle); only the pooled tile (64 pixels) is staged and stored
   int mt;             // M sub-tiles (128 pixels each) per CTA tile: one weight tile feeds mt activation tiles
   int tmem_cols;      // 2 * mt * BLOCK_N rounded to a power of two >= 32
   const float* bias;  // [Cout_pad]
@@ -100,7 +105,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   const uint32_t sEpi = p.rowshare ? sB + p.sb_slots * 2u * kBBytes
                                    : sB + S * b_stride;  // 1024-aligned: kABytes, kBBytes, a_slot are multiples of 1024
   constexpr int kPoolBytes = kABytes / 4;  // pooled tile: 32 rows x 128 B
-  const int epi_buf_bytes = (kABytes + (p.pool ? kPoolBytes : 0)) * (p.has_lo_out ? 2 : 1);
+  constexpr int kVpPlane = 64 * 128;  // vpool: pooled tile of 64 pixels x 64 channels
+  const int epi_buf_bytes = p.vpool ? kVpPlane * (p.has_lo_out ? 2 : 1)
+                                    : (kABytes + (p.pool ? kPoolBytes : 0)) * (p.has_lo_out ? 2 : 1);
   const uint32_t sMisc = sEpi + p.epi_bufs * epi_buf_bytes;
   uint8_t* misc_gen = smem_gen + (sMisc - smem_base);
   float* bias_s = reinterpret_cast<float*>(misc_gen);  // BLOCK_N floats
@@ -152,7 +159,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  const int total_tiles = (m_tiles / MT) * p.n_tiles;  // the host guarantees m_tiles % MT == 0
+  // the host guarantees m_tiles % MT == 0; in vpool mode the tile grid is already one of row pairs
+  const int total_tiles = p.vpool ? m_tiles * p.n_tiles : (m_tiles / MT) * p.n_tiles;
   const int num_kb = (p.fat ? 1 : p.num_terms) * p.taps_h * p.taps_w * p.cin_chunks;
   const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * kBlockK * 2;
   const uint32_t stage_tx = (p.fat ? 2u : 1u) * (static_cast<uint32_t>(MT) * a_box_bytes + kBBytes);
@@ -173,12 +181,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       // weight tiles [B_hi | B_lo] of the three dx taps; two independent rings.
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      const uint32_t a_tx = 2u * static_cast<uint32_t>(p.box_w + 2) * kBlockK * 2, b_tx = 2u * kBBytes;
+      const uint32_t a_tx = 2u * static_cast<uint32_t>((p.box_w + 2) * MT) * kBlockK * 2, b_tx = 2u * kBBytes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int tw, th, tn;
         m_coords(tile / p.n_tiles, tw, th, tn);
-        const int wa = tw * p.box_w - p.pad_w, ha = th - p.pad_h;
+        const int wa = tw * p.box_w - p.pad_w, ha = th * MT - p.pad_h;  // the activation box is MT rows high
         for (int dy = 0; dy < p.taps_h; ++dy) {
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
             ptx::mbar_wait(empty_bar(sa), pa ^ 1u);
@@ -224,10 +232,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       for (int term = 0; term < terms; ++term) {
         const CUtensorMap* mapA = (term == 2) ? &tmA_lo : &tmA_hi;
         const CUtensorMap* mapB = (term == 1) ? &tmB_lo : &tmB_hi;
+        // K order: dy, channel chunk, dx -- the order of the row-share mode, so that every path of this kernel
+        // accumulates a given output in the same sequence (fused / unfused variants stay bit-identical)
         for (int dy = 0; dy < p.taps_h; ++dy) {
-          for (int dx = 0; dx < p.taps_w; ++dx) {
-            const int tap = dy * p.taps_w + dx;
-            for (int cc = 0; cc < p.cin_chunks; ++cc) {
+          for (int cc = 0; cc < p.cin_chunks; ++cc) {
+            for (int dx = 0; dx < p.taps_w; ++dx) {
+              const int tap = dy * p.taps_w + dx;
               ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
               if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(full_bar(stage), stage_tx);
@@ -268,7 +278,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * 2u * BLOCK_N;
+        const uint32_t acc_w = static_cast<uint32_t>(p.wide ? 2 * BLOCK_N : BLOCK_N);
+        const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * MT) * acc_w;
+        const uint32_t sub_rows = static_cast<uint32_t>(p.box_w + 2) * 128u;  // sub-tile j starts j image rows further
         uint32_t first = 0u;  // the first MMA of the tile overwrites the accumulator
         for (int dy = 0; dy < p.taps_h; ++dy) {
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
@@ -281,12 +293,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
               if (ptx::elect_one()) {
                 // tap dx = the activation rows shifted by dx pixels: a K-major SWIZZLE_128B operand may start at any
                 // 128-byte row of a TMA-written tile (tools/umma_shift_probe.cu)
-                const uint64_t ah = ptx::umma_desc_sw128(a_hi + dx * 128), al = ptx::umma_desc_sw128(a_lo + dx * 128);
                 const uint64_t b_desc = ptx::umma_desc_sw128(sB + sb * 2u * kBBytes);
+                const uint64_t b_lo = ptx::umma_desc_sw128(sB + sb * 2u * kBBytes + kBBytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                  ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdescWide, (first | k) != 0 ? 1u : 0u);
-                  ptx::umma_bf16(d_tmem, al + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                for (int j = 0; j < 2; ++j) {
+                  if (j < MT) {
+                    const uint32_t d_tmem = d_base + static_cast<uint32_t>(j) * acc_w;
+                    const uint64_t ah = ptx::umma_desc_sw128(a_hi + j * sub_rows + dx * 128);
+                    const uint64_t al = ptx::umma_desc_sw128(a_lo + j * sub_rows + dx * 128);
+                    if (p.wide) {
+#pragma unroll
+                      for (int k = 0; k < kBlockK / 16; ++k) {
+                        ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdescWide, (first | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16(d_tmem, al + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                      }
+                    } else {
+#pragma unroll
+                      for (int k = 0; k < kBlockK / 16; ++k) {
+                        ptx::umma_bf16(d_tmem, ah + 2u * k, b_lo + 2u * k, kIdesc, (first | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16(d_tmem, al + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                        ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                      }
+                    }
+                  }
                 }
                 ptx::umma_commit(empty_bar(bi));
                 if (dx == 2) ptx::umma_commit(empty_bar(sa));
@@ -299,7 +328,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
             if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
           }
         }
-        acc ^= 1;
+        if (++acc == p.acc_sets) acc = 0;
         if (acc == 0) acc_phase ^= 1u;
       }
     }
@@ -378,6 +407,106 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
+      if constexpr (BLOCK_N >= 64 && BLOCK_N <= 128) {
+        if (p.vpool) {
+          // Fused PoolingLayer (MAX 2x2 / 2, pooling_layer.cpp:128-187) in registers.  Accumulator 0 holds image row
+          // 2 th, accumulator 1 row 2 th + 1, thread `row` owns pixel x0 + row of both.  max commutes with the
+          // (monotonic) bias add, ReLU and (hi, lo) rounding, so pooling the raw fp32 sums gives the values
+          // pool_kernel computes from the stored planes.  Vertical max: the two accumulators; horizontal max: lane ^ 1.
+          // Even lanes then convert channels [0, 32) of the pooled pixel row / 2, odd lanes channels [32, 64).
+          int tw, th, tn;
+          m_coords(tile / p.n_tiles, tw, th, tn);
+          const uint32_t acc_w = static_cast<uint32_t>(p.wide ? 2 * BLOCK_N : BLOCK_N);
+          const uint32_t t0 = tmem_base + static_cast<uint32_t>(acc * 2) * acc_w + (static_cast<uint32_t>(quarter * 32) << 16);
+          const uint32_t t1 = t0 + acc_w;
+          const int odd = lane & 1, prow = row >> 1;
+#pragma unroll 1
+          for (int chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
+            float mine[32];  // this lane's 32 channels of the pooled pixel
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {  // channels [32 hc, 32 hc + 32) of the chunk
+              uint32_t a[32], b[32];
+              ptx::tmem_ld_32x32(t0 + chunk * 64 + hc * 32, a);
+              ptx::tmem_ld_32x32(t1 + chunk * 64 + hc * 32, b);
+              if (p.wide) {
+                uint32_t ua[32], ub[32];
+                ptx::tmem_ld_32x32(t0 + BLOCK_N + chunk * 64 + hc * 32, ua);
+                ptx::tmem_ld_32x32(t1 + BLOCK_N + chunk * 64 + hc * 32, ub);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  a[i] = __float_as_uint(__uint_as_float(a[i]) + __uint_as_float(ua[i]));
+                  b[i] = __float_as_uint(__uint_as_float(b[i]) + __uint_as_float(ub[i]));
+                }
+              }
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float m = fmaxf(__uint_as_float(a[i]), __uint_as_float(b[i]));
+                m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                if (hc == odd) mine[i] = m;
+              }
+            }
+            if (issuer) {
+              if (p.epi_bufs == 1) ptx::tma_store_wait_read<0>();
+              else ptx::tma_store_wait_read<1>();
+            }
+            ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // staging buffer free; also publishes bias_s
+            const uint32_t pbuf = sEpi + ebuf * epi_buf_bytes;
+            const uint32_t prow_hi = pbuf + prow * 128, prow_lo = prow_hi + kVpPlane;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                float f0 = mine[j * 8 + 2 * q] + bias_s[chunk * 64 + odd * 32 + j * 8 + 2 * q];
+                float f1 = mine[j * 8 + 2 * q + 1] + bias_s[chunk * 64 + odd * 32 + j * 8 + 2 * q + 1];
+                if (p.relu) {
+                  f0 = fmaxf(f0, 0.f);
+                  f1 = fmaxf(f1, 0.f);
+                }
+                {
+                  // what pool_kernel sees is the STORED value hi + lo of the winning pixel; it then splits that sum
+                  // again.  Reproduce both roundings so that the pooled planes are bit-identical to the unfused path
+                  // (the two splits differ when lo is exactly half an ulp of hi).
+                  const __nv_bfloat162 s2 = __floats2bfloat162_rn(f0, f1);
+                  const uint32_t sh = *reinterpret_cast<const uint32_t*>(&s2);
+                  const float g0 = __uint_as_float(sh << 16), g1 = __uint_as_float(sh & 0xFFFF0000u);
+                  const __nv_bfloat162 t2 = __floats2bfloat162_rn(f0 - g0, f1 - g1);
+                  const uint32_t sl = *reinterpret_cast<const uint32_t*>(&t2);
+                  f0 = g0 + __uint_as_float(sl << 16);
+                  f1 = g1 + __uint_as_float(sl & 0xFFFF0000u);
+                }
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+                hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+                const __nv_bfloat162 l2 = __floats2bfloat162_rn(f0 - __uint_as_float(hi[q] << 16),
+                                                                f1 - __uint_as_float(hi[q] & 0xFFFF0000u));
+                lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
+              }
+              const uint32_t off = static_cast<uint32_t>(((odd * 4 + j) ^ (prow & 7)) << 4);  // 128B swizzle
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_hi + off), "r"(hi[0]), "r"(hi[1]),
+                           "r"(hi[2]), "r"(hi[3]) : "memory");
+              if (p.has_lo_out)
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(prow_lo + off), "r"(lo[0]), "r"(lo[1]),
+                             "r"(lo[2]), "r"(lo[3]) : "memory");
+            }
+            ptx::fence_proxy_async_smem();
+            ptx::named_bar_sync(kEpiBarId, kEpiThreads);
+            if (issuer) {
+              const int c0 = n_base + chunk * 64;
+              ptx::tma_store_4d(&tmP_hi, pbuf, c0, tw * (p.box_w >> 1), th, tn);
+              if (p.has_lo_out) ptx::tma_store_4d(&tmP_lo, pbuf + kVpPlane, c0, tw * (p.box_w >> 1), th, tn);
+              ptx::tma_store_commit();
+            }
+            if (++ebuf == p.epi_bufs) ebuf = 0;
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(tempty_bar(acc));
+          if (++acc == p.acc_sets) acc = 0;
+          if (acc == 0) acc_phase ^= 1u;
+          continue;
+        }
+      }
       for (int sub = 0; sub < MT; ++sub) {
         int tw, th, tn;
         m_coords(m0 + sub, tw, th, tn);
@@ -657,8 +786,17 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   p.pad_w = d->pad_w;
   p.cin_chunks = d->C / 64;
   pick_box(d->N, Ho, Wo, pool, &p.box_w, &p.box_h, &p.box_n);
+  // Pooled narrow-N 3x3 layers of the fp32-faithful path (conv1_2, conv2_2): row-share mode over image-row pairs
+  // with the pooling done in registers (p.vpool, see the kernel).  Tiles are 128 pixels x 2 rows.
+  const bool vpair = split && pool && !d->y_hi && BN <= 128 && d->KW == 3 && d->KH == 3 && (Wo % 128 == 0) &&
+                     !getenv("MSCNN_NO_FAT") && !getenv("MSCNN_NO_ROWSHARE") && !getenv("MSCNN_NO_VPOOL");
+  if (vpair) {
+    p.box_w = 128;
+    p.box_h = 1;
+    p.box_n = 1;
+  }
   p.tiles_w = (Wo + p.box_w - 1) / p.box_w;
-  p.tiles_h = (Ho + p.box_h - 1) / p.box_h;
+  p.tiles_h = vpair ? Ho / 2 : (Ho + p.box_h - 1) / p.box_h;
   p.tiles_n = (d->N + p.box_n - 1) / p.box_n;
   p.n_tiles = d->Cout_pad / BN;
   p.relu = d->relu;
@@ -683,6 +821,9 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   // barrier round trip covers 3x the MMAs (conv1_2: 6.3 -> 3.9 ms, profiles/r01_probe_layers*.log).
   p.fat = (split && BN <= 128 && !getenv("MSCNN_NO_FAT")) ? 1 : 0;
   p.wide = (p.fat && !getenv("MSCNN_NO_WIDE")) ? 1 : 0;
+  // vpair with BN = 128: two wide sub-tiles are 512 TMEM columns, so a single accumulator set (the epilogue of a
+  // tile is ~7 % of its MMA time there); keeps the accumulation order of the un-pooled row-share path bit for bit
+  p.acc_sets = (vpair && BN == 128 && p.wide) ? 1 : 2;
   const int acc_mul = p.wide ? 2 : 1;  // accumulator columns per sub-tile = acc_mul * BN
   // M sub-tiles per CTA tile: for narrow N one weight tile should feed several activation tiles
   // (fewer hot-line weight fetches and barrier round trips per MMA).  2 * mt * BN TMEM columns <= 512.
@@ -714,9 +855,30 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   // Row-share mode: wide mode over 128 x 1 pixel boxes with three horizontal taps.  The activation tile of a
   // (dy, channel chunk) is loaded ONCE with a one-pixel halo on each side (130 rows) and serves the three dx taps
   // through descriptor row shifts; narrow-N layers are bound by shared-memory bandwidth (TMA fill + operand
-  // reads share 128 B/clk/SM, profiles/r01g_summary.md), and this removes two of three activation fills.
+  // reads share 128 B/clk/SM, profiles/r01h_summary.md), and this removes two of three activation fills.
   size_t smem_rs = 0;
-  if (p.wide && d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !getenv("MSCNN_NO_ROWSHARE")) {
+  if (vpair) {
+    const int a_plane = ((p.box_w + 2) * 2 * 128 + 1023) / 1024 * 1024;  // two image rows of 130 pixels
+    const int a_slot = 2 * a_plane, b_slot = 2 * b_bytes;
+    const int vp_unit = 64 * 128 * (p.has_lo_out ? 2 : 1);
+    for (int eb = 2; eb >= 1 && !p.rowshare; --eb) {
+      int sb = (budget - misc - eb * vp_unit - 2 * a_slot) / b_slot;
+      if (sb > 4) sb = 4;
+      if (sb >= 2) {
+        p.rowshare = 1;
+        p.vpool = 1;
+        p.sa_slots = 2;
+        p.sb_slots = sb;
+        p.a_slot = a_slot;
+        epi_bufs = eb;
+        stages = 2 + sb;
+        mt = 2;
+        smem_rs = (size_t)2 * a_slot + (size_t)sb * b_slot + (size_t)eb * vp_unit + misc;
+      }
+    }
+    if (!p.rowshare) return MSCNN_ERR_INVALID;
+  }
+  if (!vpair && p.wide && d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !getenv("MSCNN_NO_ROWSHARE")) {
     const int a_plane = ((p.box_w + 2) * 128 + 1023) / 1024 * 1024;
     const int a_slot = 2 * a_plane, b_slot = 2 * b_bytes;
     for (int eb = (epi_unit == 0 ? 0 : 2); eb >= (epi_unit == 0 ? 0 : 1) && !p.rowshare; --eb) {
@@ -739,20 +901,20 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   }
   p.mt = mt;
   int tcols = 32;
-  while (tcols < 2 * mt * BN * acc_mul) tcols <<= 1;
+  while (tcols < p.acc_sets * mt * BN * acc_mul) tcols <<= 1;
   p.tmem_cols = tcols;
   p.stages = stages;
   p.epi_bufs = epi_bufs;  // 0 in fp32-output mode: no staging region is carved
   const size_t smem = p.rowshare ? smem_rs : (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
   if (getenv("MSCNN_VERBOSE_CONV"))
-    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d rowshare=%d(%d+%d) terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
-            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.num_terms, stages,
+    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d rowshare=%d(%d+%d) vpool=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
+            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.vpool, p.num_terms, stages,
             epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
   CUtensorMap maps[8];
   memset(maps, 0, sizeof(maps));
   const uint32_t obox[4] = {64u, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
-  const uint32_t abox[4] = {64u, (uint32_t)(p.box_w + (p.rowshare ? 2 : 0)), (uint32_t)p.box_h, (uint32_t)p.box_n};
+  const uint32_t abox[4] = {64u, (uint32_t)(p.box_w + (p.rowshare ? 2 : 0)), (uint32_t)(p.vpool ? 2 : p.box_h), (uint32_t)p.box_n};
   const uint64_t adim[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
   int rc = tmap_nhwc_bf16(&maps[0], d->x_hi, adim, abox);
   if (rc) return rc;
@@ -793,7 +955,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   maps[7] = maps[5];
   if (p.pool) {
     const uint64_t pdim[4] = {(uint64_t)d->Cout_pad, (uint64_t)(Wo / 2), (uint64_t)(Ho / 2), (uint64_t)d->N};
-    const uint32_t pbox[4] = {64u, (uint32_t)(p.box_w / 2), (uint32_t)(p.box_h / 2), (uint32_t)p.box_n};
+    const uint32_t pbox[4] = {64u, (uint32_t)(p.box_w / 2), (uint32_t)(p.vpool ? 1 : p.box_h / 2), (uint32_t)p.box_n};
     rc = tmap_nhwc_bf16(&maps[6], d->pool_hi, pdim, pbox);
     if (rc) return rc;
     if (p.has_lo_out) {
@@ -804,7 +966,8 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
     }
   }
 
-  const int total_tiles = p.tiles_w * p.tiles_h * p.tiles_n / p.mt * p.n_tiles;
+  const int total_tiles = p.vpool ? p.tiles_w * p.tiles_h * p.tiles_n * p.n_tiles
+                                  : p.tiles_w * p.tiles_h * p.tiles_n / p.mt * p.n_tiles;
   int grid = mscnn_sm_count();
   if (grid > total_tiles) grid = total_tiles;
   cudaError_t e;

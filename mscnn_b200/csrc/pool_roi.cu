@@ -38,7 +38,7 @@ __device__ __forceinline__ Vec8 load8(const __nv_bfloat16* hi, const __nv_bfloat
 
 // STREAM: st.global.cs (evict-first).  ROI pooling writes 2.6 GB per batch while gathering from a 63 MB per-image
 // feature map that should stay in the 126 MB L2; with default stores the output stream evicted it and DRAM
-// read 3.7 GB per launch instead of 0.5 GB (profiles/r01e_roi_pool.md).
+// read 3.7 GB per launch instead of 0.5 GB (profiles/r01h_summary.md).
 template <bool STREAM = false>
 __device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, size_t off, const Vec8& x) {
   uint4 a, b;
@@ -166,7 +166,7 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
       // 16-byte units, 32-bit indices (the feature map has < 2^31 / 8 elements: checked by the launcher).  The
       // window is walked as one flattened pixel sequence, two pixels per step, and a lane owns channel groups g and
       // g + 32 at once (C = 512: cg = 64), so up to eight 16-byte loads are in flight per lane: the kernel was
-      // bound by the latency of two (profiles/r01g_roi_pool.md).  fmaxf gives the reference's
+      // bound by the latency of two (profiles/r01h_summary.md).  fmaxf gives the reference's
       // `if (x > max) max = x` result for every non-NaN input.
       const uint4* xh4 = reinterpret_cast<const uint4*>(xh);
       const uint4* xl4 = reinterpret_cast<const uint4*>(xl);

@@ -243,15 +243,18 @@ class Net:
                    "net_detect_cascade")
 
 
-def kitti_detect_cfg(net_h: int, net_w: int, max_rois: int = 2000, num_cls: int = 5, cls_id: int = 2) -> capi.DetectCfg:
-    """Post-process settings of examples/kitti_car/run_mscnn_detection.m:42-50 with ratios = 1."""
+def kitti_detect_cfg(net_h: int, net_w: int, max_rois: int = 2000, num_cls: int = 5, cls_id: int = 2,
+                     org_hw: tuple[int, int] | None = None) -> capi.DetectCfg:
+    """Post-process settings of examples/kitti_car/run_mscnn_detection.m:42-50; org_hw = size of the original
+    image (`ratios = [imgH imgW] ./ [orgH orgW]`, :62-63), default = the net size (ratios = 1)."""
     cfg = capi.DetectCfg()
     cfg.num_cls, cfg.cls_id = num_cls, cls_id
     for k, v in enumerate([0.1, 0.1, 0.2, 0.2]):
         cfg.bbox_std[k] = v
         cfg.bbox_mean[k] = 0.0
     cfg.proposal_thr, cfg.nms_overlap = -10.0, 0.5
-    cfg.ratio_h = cfg.ratio_w = 1.0
-    cfg.org_h, cfg.org_w = float(net_h), float(net_w)
+    oh, ow = org_hw if org_hw is not None else (net_h, net_w)
+    cfg.ratio_h, cfg.ratio_w = net_h / oh, net_w / ow
+    cfg.org_h, cfg.org_w = float(oh), float(ow)
     cfg.max_rois_per_image = max_rois
     return cfg

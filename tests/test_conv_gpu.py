@@ -215,7 +215,9 @@ def test_conv1_1_tensor_core(cuda, split, shape):
 
 
 @pytest.mark.parametrize("split", [True, False], ids=["split", "bf16"])
-@pytest.mark.parametrize("shape", [(2, 64, 64, 192, 64), (1, 64, 128, 320, 128), (2, 128, 24, 80, 256), (3, 64, 10, 12, 64)])
+@pytest.mark.parametrize("shape", [(2, 64, 64, 192, 64), (1, 64, 128, 320, 128), (2, 128, 24, 80, 256), (3, 64, 10, 12, 64),
+                                   # W % 128 == 0, narrow N: row-pair tiles with the pooling done in registers
+                                   (1, 64, 8, 256, 64), (2, 128, 6, 128, 128), (2, 64, 64, 512, 64), (1, 64, 32, 384, 128)])
 def test_conv_fused_pool(cuda, split, shape):
     """mscnn_conv_forward with pool_hi set == conv followed by mscnn_pool_forward, bit for bit; the
     pool-only form (no un-pooled store) gives the same pooled planes."""
