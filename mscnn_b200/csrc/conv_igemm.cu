@@ -56,6 +56,9 @@ struct IgemmParams {
                       // (dy, channel chunk) serves the three dx taps through descriptor row shifts; activation and
                       // weight tiles travel in separate rings (sa_slots x a_slot bytes, sb_slots x 2 weight tiles)
   int sa_slots, sb_slots, a_slot;
+  int a_taps;         // two-ring engine: 3 = one activation slot serves the three dx taps (row shifts), 1 = one slot per tap
+  int b_split;        // two-ring engine, BLOCK_N = 256: a weight slot holds ONE tile; B_hi and B_lo of a tap follow each other
+  int b_slot;         // bytes per weight slot
   int acc_sets;       // TMEM accumulator sets: 2 (epilogue of tile i overlaps the MMAs of tile i + 1) or, when two wide
                       // sub-tiles of BLOCK_N = 128 already fill the 512 columns, 1 (vpool mode only)
   int vpool;          // row-share mode over image-row PAIRS (mt = 2: sub-tile j = row 2 th + j) with the 2x2 MAX pooling
@@ -102,7 +105,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   const uint32_t b_stride = p.fat ? 2u * kBBytes : kBBytes;  //            [B_hi] or [B_hi][B_lo]
   const uint32_t sA = smem_base;
   const uint32_t sB = p.rowshare ? sA + p.sa_slots * p.a_slot : sA + S * a_stride;
-  const uint32_t sEpi = p.rowshare ? sB + p.sb_slots * 2u * kBBytes
+  const uint32_t sEpi = p.rowshare ? sB + p.sb_slots * p.b_slot
                                    : sB + S * b_stride;  // 1024-aligned: kABytes, kBBytes, a_slot are multiples of 1024
   constexpr int kPoolBytes = kABytes / 4;  // pooled tile: 32 rows x 128 B
   constexpr int kVpPlane = 64 * 128;  // vpool: pooled tile of 64 pixels x 64 channels
@@ -177,39 +180,51 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     // ------------------------------------------------------------ TMA producer
     // The whole warp walks the loops (warp-uniform control flow); one elected lane issues.
     if (p.rowshare) {
-      // Row-share mode (MT == 1, 128x1 boxes): per (dy, channel chunk) one activation tile of 130 pixels, then the
-      // weight tiles [B_hi | B_lo] of the three dx taps; two independent rings.
+      // Two-ring engine: activation pairs (A_hi, A_lo) and weight tiles travel in separate rings, each operand tile of
+      // a (tap, channel chunk) is fetched ONCE for the three products hi*hi, hi*lo, lo*hi.  a_taps == 3 (128x1 boxes,
+      // three horizontal taps): the activation slot holds box_w + 2 pixels and serves the dx taps by row shifts.
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      const uint32_t a_tx = 2u * static_cast<uint32_t>((p.box_w + 2) * MT) * kBlockK * 2, b_tx = 2u * kBBytes;
+      const int halo = p.a_taps == 3 ? 2 : 0;
+      const uint32_t a_tx = 2u * static_cast<uint32_t>((p.box_w + halo) * p.box_h * p.box_n * (p.vpool ? 2 : 1)) * kBlockK * 2;
+      const uint32_t b_tx = p.b_split ? kBBytes : 2u * kBBytes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int tw, th, tn;
         m_coords(tile / p.n_tiles, tw, th, tn);
-        const int wa = tw * p.box_w - p.pad_w, ha = th * MT - p.pad_h;  // the activation box is MT rows high
+        const int wa = tw * p.box_w - p.pad_w, ha = th * (p.vpool ? 2 : p.box_h) - p.pad_h, na = tn * p.box_n;
         for (int dy = 0; dy < p.taps_h; ++dy) {
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
-            ptx::mbar_wait(empty_bar(sa), pa ^ 1u);
-            if (ptx::elect_one()) {
-              ptx::mbar_expect_tx(full_bar(sa), a_tx);
-              const uint32_t a0 = sA + sa * p.a_slot;
-              ptx::tma_load_4d(a0, &tmA_hi, full_bar(sa), cc * kBlockK, wa, ha + dy, tn);
-              ptx::tma_load_4d(a0 + p.a_slot / 2, &tmA_lo, full_bar(sa), cc * kBlockK, wa, ha + dy, tn);
-            }
-            __syncwarp();
-            if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
-            for (int dx = 0; dx < 3; ++dx) {
-              const int bi = p.sa_slots + sb;
-              ptx::mbar_wait(empty_bar(bi), pb ^ 1u);
-              if (ptx::elect_one()) {
-                ptx::mbar_expect_tx(full_bar(bi), b_tx);
-                const uint32_t b0 = sB + sb * 2u * kBBytes;
-                const int kcol = ((dy * 3 + dx) * p.cin_chunks + cc) * kBlockK;
-                ptx::tma_load_2d(b0, &tmB_hi, full_bar(bi), kcol, n_tile * BLOCK_N);
-                ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
+            for (int dx = 0; dx < p.taps_w; ++dx) {
+              if (p.a_taps == 1 || dx == 0) {
+                ptx::mbar_wait(empty_bar(sa), pa ^ 1u);
+                if (ptx::elect_one()) {
+                  ptx::mbar_expect_tx(full_bar(sa), a_tx);
+                  const uint32_t a0 = sA + sa * p.a_slot;
+                  const int wx = wa + (p.a_taps == 1 ? dx : 0);
+                  ptx::tma_load_4d(a0, &tmA_hi, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
+                  ptx::tma_load_4d(a0 + p.a_slot / 2, &tmA_lo, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
+                }
+                __syncwarp();
+                if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
               }
-              __syncwarp();
-              if (++sb == p.sb_slots) { sb = 0; pb ^= 1u; }
+              const int kcol = ((dy * p.taps_w + dx) * p.cin_chunks + cc) * kBlockK;
+              for (int half = 0; half < (p.b_split ? 2 : 1); ++half) {
+                const int bi = p.sa_slots + sb;
+                ptx::mbar_wait(empty_bar(bi), pb ^ 1u);
+                if (ptx::elect_one()) {
+                  ptx::mbar_expect_tx(full_bar(bi), b_tx);
+                  const uint32_t b0 = sB + sb * p.b_slot;
+                  if (p.b_split) {
+                    ptx::tma_load_2d(b0, half == 0 ? &tmB_hi : &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
+                  } else {
+                    ptx::tma_load_2d(b0, &tmB_hi, full_bar(bi), kcol, n_tile * BLOCK_N);
+                    ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
+                  }
+                }
+                __syncwarp();
+                if (++sb == p.sb_slots) { sb = 0; pb ^= 1u; }
+              }
             }
           }
         }
@@ -280,52 +295,91 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         ptx::tc_fence_after();
         const uint32_t acc_w = static_cast<uint32_t>(p.wide ? 2 * BLOCK_N : BLOCK_N);
         const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * MT) * acc_w;
-        const uint32_t sub_rows = static_cast<uint32_t>(p.box_w + 2) * 128u;  // sub-tile j starts j image rows further
+        const uint32_t sub_rows = static_cast<uint32_t>(p.box_w + 2) * 128u;  // vpool: sub-tile j starts j image rows further
         uint32_t first = 0u;  // the first MMA of the tile overwrites the accumulator
+        uint32_t a_hi = 0, a_lo = 0;
         for (int dy = 0; dy < p.taps_h; ++dy) {
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
-            ptx::mbar_wait(full_bar(sa), pa);
-            const uint32_t a_hi = sA + sa * p.a_slot, a_lo = a_hi + p.a_slot / 2;
-            for (int dx = 0; dx < 3; ++dx) {
-              const int bi = p.sa_slots + sb;
-              ptx::mbar_wait(full_bar(bi), pb);
-              ptx::tc_fence_after();
-              if (ptx::elect_one()) {
-                // tap dx = the activation rows shifted by dx pixels: a K-major SWIZZLE_128B operand may start at any
-                // 128-byte row of a TMA-written tile (tools/umma_shift_probe.cu)
-                const uint64_t b_desc = ptx::umma_desc_sw128(sB + sb * 2u * kBBytes);
-                const uint64_t b_lo = ptx::umma_desc_sw128(sB + sb * 2u * kBBytes + kBBytes);
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                  if (j < MT) {
-                    const uint32_t d_tmem = d_base + static_cast<uint32_t>(j) * acc_w;
-                    const uint64_t ah = ptx::umma_desc_sw128(a_hi + j * sub_rows + dx * 128);
-                    const uint64_t al = ptx::umma_desc_sw128(a_lo + j * sub_rows + dx * 128);
-                    if (p.wide) {
+            for (int dx = 0; dx < p.taps_w; ++dx) {
+              if (p.a_taps == 1 || dx == 0) {
+                ptx::mbar_wait(full_bar(sa), pa);
+                a_hi = sA + sa * p.a_slot;
+                a_lo = a_hi + p.a_slot / 2;
+              }
+              // tap dx = the activation rows shifted by dx pixels: a K-major SWIZZLE_128B operand may start at any
+              // 128-byte row of a TMA-written tile (tools/umma_shift_probe.cu)
+              const uint32_t shift = p.a_taps == 3 ? static_cast<uint32_t>(dx) * 128u : 0u;
+              const bool a_done = (p.a_taps == 1) || (dx == p.taps_w - 1);
+              const bool last = (dy == p.taps_h - 1) && (cc == p.cin_chunks - 1) && (dx == p.taps_w - 1);
+              const int sa_now = sa;
+              if (p.b_split) {
+                // weight slot 1: B_hi -> lo*hi and hi*hi; weight slot 2: B_lo -> hi*lo
+                for (int half = 0; half < 2; ++half) {
+                  const int bi = p.sa_slots + sb;
+                  ptx::mbar_wait(full_bar(bi), pb);
+                  ptx::tc_fence_after();
+                  if (ptx::elect_one()) {
+                    const uint64_t b_desc = ptx::umma_desc_sw128(sB + sb * p.b_slot);
+                    const uint64_t ah = ptx::umma_desc_sw128(a_hi + shift), al = ptx::umma_desc_sw128(a_lo + shift);
+                    if (half == 0) {
 #pragma unroll
                       for (int k = 0; k < kBlockK / 16; ++k) {
-                        ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdescWide, (first | k) != 0 ? 1u : 0u);
-                        ptx::umma_bf16(d_tmem, al + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                        ptx::umma_bf16(d_base, al + 2u * k, b_desc + 2u * k, kIdesc, (first | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16(d_base, ah + 2u * k, b_desc + 2u * k, kIdesc, 1u);
                       }
                     } else {
 #pragma unroll
-                      for (int k = 0; k < kBlockK / 16; ++k) {
-                        ptx::umma_bf16(d_tmem, ah + 2u * k, b_lo + 2u * k, kIdesc, (first | k) != 0 ? 1u : 0u);
-                        ptx::umma_bf16(d_tmem, al + 2u * k, b_desc + 2u * k, kIdesc, 1u);
-                        ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                      for (int k = 0; k < kBlockK / 16; ++k) ptx::umma_bf16(d_base, ah + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                    }
+                    ptx::umma_commit(empty_bar(bi));
+                    if (half == 1 && a_done) ptx::umma_commit(empty_bar(sa_now));
+                    if (half == 1 && last) ptx::umma_commit(tfull_bar(acc));
+                  }
+                  __syncwarp();
+                  first = 1u;
+                  if (++sb == p.sb_slots) { sb = 0; pb ^= 1u; }
+                }
+              } else {
+                const int bi = p.sa_slots + sb;
+                ptx::mbar_wait(full_bar(bi), pb);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                  const uint64_t b_desc = ptx::umma_desc_sw128(sB + sb * p.b_slot);
+                  const uint64_t b_lo = ptx::umma_desc_sw128(sB + sb * p.b_slot + kBBytes);
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    if (j < MT) {
+                      const uint32_t d_tmem = d_base + static_cast<uint32_t>(j) * acc_w;
+                      const uint64_t ah = ptx::umma_desc_sw128(a_hi + j * sub_rows + shift);
+                      const uint64_t al = ptx::umma_desc_sw128(a_lo + j * sub_rows + shift);
+                      if (p.wide) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                          ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdescWide, (first | k) != 0 ? 1u : 0u);
+                          ptx::umma_bf16(d_tmem, al + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                        }
+                      } else {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                          ptx::umma_bf16(d_tmem, ah + 2u * k, b_lo + 2u * k, kIdesc, (first | k) != 0 ? 1u : 0u);
+                          ptx::umma_bf16(d_tmem, al + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                          ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdesc, 1u);
+                        }
                       }
                     }
                   }
+                  ptx::umma_commit(empty_bar(bi));
+                  if (a_done) ptx::umma_commit(empty_bar(sa_now));
+                  if (last) ptx::umma_commit(tfull_bar(acc));
                 }
-                ptx::umma_commit(empty_bar(bi));
-                if (dx == 2) ptx::umma_commit(empty_bar(sa));
-                if (dx == 2 && dy == p.taps_h - 1 && cc == p.cin_chunks - 1) ptx::umma_commit(tfull_bar(acc));
+                __syncwarp();
+                first = 1u;
+                if (++sb == p.sb_slots) { sb = 0; pb ^= 1u; }
               }
-              __syncwarp();
-              first = 1u;
-              if (++sb == p.sb_slots) { sb = 0; pb ^= 1u; }
+              if (a_done) {
+                if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
+              }
             }
-            if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
           }
         }
         if (++acc == p.acc_sets) acc = 0;
@@ -866,6 +920,9 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
       if (sb > 4) sb = 4;
       if (sb >= 2) {
         p.rowshare = 1;
+        p.a_taps = 3;
+        p.b_split = 0;
+        p.b_slot = b_slot;
         p.vpool = 1;
         p.sa_slots = 2;
         p.sb_slots = sb;
@@ -888,6 +945,9 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
         if (sb > 5) sb = 5;
         if (sb >= 3) {
           p.rowshare = 1;
+          p.a_taps = 3;
+          p.b_split = 0;
+          p.b_slot = b_slot;
           p.sa_slots = sa;
           p.sb_slots = sb;
           p.a_slot = a_slot;
@@ -899,6 +959,34 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
       }
     }
   }
+  // BLOCK_N = 256, fp32-faithful: the same two-ring engine with single-tile weight slots.  The term-major loop of the
+  // non-fat path fetches A_hi and B_hi twice per (tap, channel chunk) (144 KB of TMA fills); here the activation pair and
+  // both weight tiles are fetched once (96 KB; 76 KB with the row-share halo on 128 x 1 boxes): a third less L2->SM and
+  // shared-memory fill traffic on the layers that hold 70 % of the step and run against the power cap.
+  if (split && BN == 256 && !getenv("MSCNN_NO_RING256")) {
+    const bool halo = (d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !getenv("MSCNN_NO_ROWSHARE"));
+    const int a_plane = halo ? ((p.box_w + 2) * 128 + 1023) / 1024 * 1024 : kABytes;
+    const int a_slot = 2 * a_plane, b_slot = b_bytes;
+    const int eb = (epi_unit == 0) ? 0 : 1;
+    const int rings = budget - misc - eb * epi_unit;
+    for (int sa = 3; sa >= 2 && !p.rowshare; --sa) {
+      int sb = (rings - sa * a_slot) / b_slot;
+      if (sb > 4) sb = 4;
+      if (sb >= 3) {
+        p.rowshare = 1;
+        p.a_taps = halo ? 3 : 1;
+        p.b_split = 1;
+        p.b_slot = b_slot;
+        p.sa_slots = sa;
+        p.sb_slots = sb;
+        p.a_slot = a_slot;
+        epi_bufs = eb;
+        stages = sa + sb;
+        mt = 1;
+        smem_rs = (size_t)sa * a_slot + (size_t)sb * b_slot + (size_t)eb * epi_unit + misc;
+      }
+    }
+  }
   p.mt = mt;
   int tcols = 32;
   while (tcols < p.acc_sets * mt * BN * acc_mul) tcols <<= 1;
@@ -907,14 +995,14 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   p.epi_bufs = epi_bufs;  // 0 in fp32-output mode: no staging region is carved
   const size_t smem = p.rowshare ? smem_rs : (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
   if (getenv("MSCNN_VERBOSE_CONV"))
-    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d rowshare=%d(%d+%d) vpool=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
-            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.vpool, p.num_terms, stages,
+    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d rowshare=%d(%d+%d) vpool=%d a_taps=%d b_split=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
+            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.vpool, p.a_taps, p.b_split, p.num_terms, stages,
             epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
   CUtensorMap maps[8];
   memset(maps, 0, sizeof(maps));
   const uint32_t obox[4] = {64u, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
-  const uint32_t abox[4] = {64u, (uint32_t)(p.box_w + (p.rowshare ? 2 : 0)), (uint32_t)(p.vpool ? 2 : p.box_h), (uint32_t)p.box_n};
+  const uint32_t abox[4] = {64u, (uint32_t)(p.box_w + (p.a_taps == 3 ? 2 : 0)), (uint32_t)(p.vpool ? 2 : p.box_h), (uint32_t)p.box_n};
   const uint64_t adim[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
   int rc = tmap_nhwc_bf16(&maps[0], d->x_hi, adim, abox);
   if (rc) return rc;
