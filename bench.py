@@ -363,9 +363,9 @@ def main() -> None:
                      "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                      # mean dram__bytes_read + dram__bytes_write per launch of the convolution kernels
                      # (conv_igemm_kernel<*> + conv_c3_tc_kernel, 378 launches = 14 forwards) from the committed ncu
-                     # launch list profiles/r01h_launches.csv; per-layer `ncu --set full` captures (conv3_2: 1.02 GB +
-                     # 0.97 GB = its algorithmic 2.01 GB of planes in + out) in profiles/r01h_summary.md
-                     "traffic": 1.342e9, "traffic_source": "profiles/r01h_launches.csv (mean over the step's conv launches)",
+                     # launch list profiles/r01i_launches.csv; per-layer `ncu --set full` captures (conv3_2: 1.02 GB +
+                     # 0.97 GB = its algorithmic 2.01 GB of planes in + out) in profiles/r01h_summary.md / r01i_summary.md
+                     "traffic": 1.266e+09, "traffic_source": "profiles/r01i_launches.csv (mean over the step's conv launches)",
                      "algorithmic_gflop_per_step": r["flops"] / 1e9,
                      "launches_per_step": r["conv_launches"],
                      "avg_launch_ms": r["conv_ms"] / r["conv_launches"],

@@ -186,8 +186,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const int halo = p.a_taps == 3 ? 2 : 0;
-      const uint32_t a_tx = 2u * static_cast<uint32_t>((p.box_w + halo) * p.box_h * p.box_n * (p.vpool ? 2 : 1)) * kBlockK * 2;
-      const uint32_t b_tx = p.b_split ? kBBytes : 2u * kBBytes;
+      const bool single = (p.num_terms == 1);  // plain bf16 path: no lo planes anywhere
+      const uint32_t a_tx = (single ? 1u : 2u) * static_cast<uint32_t>((p.box_w + halo) * p.box_h * p.box_n * (p.vpool ? 2 : 1)) * kBlockK * 2;
+      const uint32_t b_tx = (p.b_split || single) ? kBBytes : 2u * kBBytes;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         int tw, th, tn;
@@ -203,7 +204,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   const uint32_t a0 = sA + sa * p.a_slot;
                   const int wx = wa + (p.a_taps == 1 ? dx : 0);
                   ptx::tma_load_4d(a0, &tmA_hi, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
-                  ptx::tma_load_4d(a0 + p.a_slot / 2, &tmA_lo, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
+                  if (!single) ptx::tma_load_4d(a0 + p.a_slot / 2, &tmA_lo, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
                 }
                 __syncwarp();
                 if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
@@ -219,7 +220,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                     ptx::tma_load_2d(b0, half == 0 ? &tmB_hi : &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
                   } else {
                     ptx::tma_load_2d(b0, &tmB_hi, full_bar(bi), kcol, n_tile * BLOCK_N);
-                    ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
+                    if (!single) ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
                   }
                 }
                 __syncwarp();
@@ -352,7 +353,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                       const uint32_t d_tmem = d_base + static_cast<uint32_t>(j) * acc_w;
                       const uint64_t ah = ptx::umma_desc_sw128(a_hi + j * sub_rows + shift);
                       const uint64_t al = ptx::umma_desc_sw128(a_lo + j * sub_rows + shift);
-                      if (p.wide) {
+                      if (p.num_terms == 1) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                          ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdesc, (first | k) != 0 ? 1u : 0u);
+                      } else if (p.wide) {
 #pragma unroll
                         for (int k = 0; k < kBlockK / 16; ++k) {
                           ptx::umma_bf16(d_tmem, ah + 2u * k, b_desc + 2u * k, kIdescWide, (first | k) != 0 ? 1u : 0u);
@@ -842,8 +847,9 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   pick_box(d->N, Ho, Wo, pool, &p.box_w, &p.box_h, &p.box_n);
   // Pooled narrow-N 3x3 layers of the fp32-faithful path (conv1_2, conv2_2): row-share mode over image-row pairs
   // with the pooling done in registers (p.vpool, see the kernel).  Tiles are 128 pixels x 2 rows.
-  const bool vpair = split && pool && !d->y_hi && BN <= 128 && d->KW == 3 && d->KH == 3 && (Wo % 128 == 0) &&
-                     !getenv("MSCNN_NO_FAT") && !getenv("MSCNN_NO_ROWSHARE") && !getenv("MSCNN_NO_VPOOL");
+  const bool vpair = pool && !d->y_hi && BN <= 128 && d->KW == 3 && d->KH == 3 && (Wo % 128 == 0) &&
+                     !getenv("MSCNN_NO_FAT") && !getenv("MSCNN_NO_ROWSHARE") && !getenv("MSCNN_NO_VPOOL") &&
+                     (split || !getenv("MSCNN_NO_BF16_RINGS"));
   if (vpair) {
     p.box_w = 128;
     p.box_h = 1;
@@ -913,11 +919,11 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   size_t smem_rs = 0;
   if (vpair) {
     const int a_plane = ((p.box_w + 2) * 2 * 128 + 1023) / 1024 * 1024;  // two image rows of 130 pixels
-    const int a_slot = 2 * a_plane, b_slot = 2 * b_bytes;
+    const int a_slot = (split ? 2 : 1) * a_plane, b_slot = (split ? 2 : 1) * b_bytes;
     const int vp_unit = 64 * 128 * (p.has_lo_out ? 2 : 1);
     for (int eb = 2; eb >= 1 && !p.rowshare; --eb) {
       int sb = (budget - misc - eb * vp_unit - 2 * a_slot) / b_slot;
-      if (sb > 4) sb = 4;
+      if (sb > 6) sb = 6;
       if (sb >= 2) {
         p.rowshare = 1;
         p.a_taps = 3;
@@ -935,14 +941,17 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
     }
     if (!p.rowshare) return MSCNN_ERR_INVALID;
   }
-  if (!vpair && p.wide && d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !getenv("MSCNN_NO_ROWSHARE")) {
+  const bool bf16_rings = !split && !getenv("MSCNN_NO_BF16_RINGS");  // plain bf16: same engine, single planes
+  if (!vpair && (p.wide || bf16_rings) && d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool &&
+      !getenv("MSCNN_NO_ROWSHARE")) {
     const int a_plane = ((p.box_w + 2) * 128 + 1023) / 1024 * 1024;
-    const int a_slot = 2 * a_plane, b_slot = 2 * b_bytes;
+    const int a_slot = (split ? 2 : 1) * a_plane, b_slot = (split ? 2 : 1) * b_bytes;
     for (int eb = (epi_unit == 0 ? 0 : 2); eb >= (epi_unit == 0 ? 0 : 1) && !p.rowshare; --eb) {
       const int rings = budget - misc - eb * epi_unit;
       for (int sa = 3; sa >= 2 && !p.rowshare; --sa) {
         int sb = (rings - sa * a_slot) / b_slot;
         if (sb > 5) sb = 5;
+        if (sa + sb > 8) sb = 8 - sa;
         if (sb >= 3) {
           p.rowshare = 1;
           p.a_taps = 3;
