@@ -34,6 +34,12 @@ struct NetHandle {
   }
 };
 NetHandle* H(void* h) { return static_cast<NetHandle*>(h); }
+// A synchronous input write issued after an asynchronous upload must land after it (the newer write wins).
+int settle_pending(NetHandle* nh) {
+  if (!nh->pending_input) return MSCNN_OK;
+  nh->pending_input = false;
+  return cudaStreamWaitEvent(Caffe::stream(), nh->input_ready, 0) == cudaSuccess ? MSCNN_OK : MSCNN_ERR_CUDA;
+}
 int fill_shape(const std::vector<int>& s, int* shape4) {
   for (size_t d = 0; d < s.size() && d < 4; ++d) shape4[d] = s[d];
   return (int)s.size();
@@ -184,6 +190,7 @@ int mscnn_net_set_blob(void* h, const char* name, const float* host, long count)
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   Blob<float>* b = H(h)->net->blob_by_name(name).get();
   if (b->count() != count) return MSCNN_ERR_INVALID;
+  if (settle_pending(H(h)) != MSCNN_OK) return MSCNN_ERR_CUDA;
   float* dst = b->mutable_gpu_data();
   return cudaMemcpyAsync(dst, host, sizeof(float) * count, cudaMemcpyHostToDevice, Caffe::stream()) == cudaSuccess
              ? MSCNN_OK
@@ -196,12 +203,14 @@ int mscnn_net_set_input_images(void* h, const char* name, void* plan, int N, con
   if (mscnn_preprocess_get_desc(plan, &d) != MSCNN_OK) return MSCNN_ERR_INVALID;
   Blob<float>* b = H(h)->net->blob_by_name(name).get();
   if (b->count() != (long)N * 3 * d.out_h * d.out_w) return MSCNN_ERR_INVALID;
+  if (settle_pending(H(h)) != MSCNN_OK) return MSCNN_ERR_CUDA;
   return mscnn_preprocess_forward_host(plan, N, host_images, b->mutable_gpu_data(), Caffe::stream());
 }
 int mscnn_net_set_blob_device(void* h, const char* name, const float* dev, long count) {
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   Blob<float>* b = H(h)->net->blob_by_name(name).get();
   if (b->count() != count) return MSCNN_ERR_INVALID;
+  if (settle_pending(H(h)) != MSCNN_OK) return MSCNN_ERR_CUDA;
   return cudaMemcpyAsync(b->mutable_gpu_data(), dev, sizeof(float) * count, cudaMemcpyDeviceToDevice,
                          Caffe::stream()) == cudaSuccess
              ? MSCNN_OK
@@ -228,24 +237,26 @@ int mscnn_net_forward(void* h, int from, int to) {
   if (to < 0) to = (int)net->layers().size() - 1;
   if (from < 0 || from > to || to >= (int)net->layers().size()) return MSCNN_ERR_INVALID;
   if (nh->pending_input) {
-    // the upload issued by mscnn_net_set_blob_async must land before the first layer runs; once the last
-    // layer that reads the blob has been queued, the next upload may overwrite it
+    // the upload issued by mscnn_net_set_blob_async must land before the first layer runs
     if (cudaStreamWaitEvent(Caffe::stream(), nh->input_ready, 0) != cudaSuccess) return MSCNN_ERR_CUDA;
     nh->pending_input = false;
-    const int c = nh->pending_consumer;
-    if (c >= from && c < to) {
-      net->ForwardFromTo(from, c);
-      if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess) return MSCNN_ERR_CUDA;
-      nh->consumed_valid = true;
-      net->ForwardFromTo(c + 1, to);
-      return MSCNN_OK;
-    }
+  }
+  if (!nh->copy_stream) {  // asynchronous uploads never used on this net: nothing to order
     net->ForwardFromTo(from, to);
-    if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess) return MSCNN_ERR_CUDA;
-    nh->consumed_valid = true;
     return MSCNN_OK;
   }
-  net->ForwardFromTo(from, to);
+  // Every forward records the point after which the input blob may be overwritten by the next asynchronous upload:
+  // right behind the last layer that reads it.
+  const int c = nh->pending_consumer;
+  if (c >= from && c < to) {
+    net->ForwardFromTo(from, c);
+    if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess) return MSCNN_ERR_CUDA;
+    net->ForwardFromTo(c + 1, to);
+  } else {
+    net->ForwardFromTo(from, to);
+    if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess) return MSCNN_ERR_CUDA;
+  }
+  nh->consumed_valid = true;
   return MSCNN_OK;
 }
 // host -> blob on a separate copy stream: returns immediately; the copy starts as soon as the layers of the

@@ -22,6 +22,18 @@
 //     direct fp32 NCHW stores for the narrow proposal / prediction heads).
 //   * persistent CTAs (one per SM), static round-robin tile schedule, n-tile fastest so
 //     CTAs working on the same pixels share the activation tile through L2.
+//   * operand delivery is what bounds these layers (TMA fills and UMMA operand reads share the 128 B/clk
+//     shared-memory port; the N = 256 layers also run against the board's power cap), so the fp32-faithful
+//     path moves every operand tile ONCE per (tap, channel chunk):
+//       - "fat" stages / "wide-B" (BLOCK_N <= 128): A_hi, A_lo, B_hi, B_lo in one stage, A_hi x [B_hi | B_lo] as one
+//         MMA of N = 2 BLOCK_N into two accumulators that the epilogue adds, plus A_lo x B_hi;
+//       - two-ring engine: activation pairs and weight tiles in separate rings; "row-share" (128 x 1 pixel boxes,
+//         three horizontal taps): one activation tile of 130 pixels per (dy, chunk), the dx taps are UMMA
+//         descriptors that start dx rows further (tools/umma_shift_probe.cu); BLOCK_N = 256: single-tile weight
+//         slots, B_hi -> lo*hi + hi*hi, B_lo -> hi*lo;
+//       - "vpool": tiles of two image rows x 128 pixels whose 2x2 max pooling happens in registers (vertical: the
+//         two accumulators, horizontal: lane ^ 1), bit-identical to conv -> store -> pool_kernel.
+//     All paths accumulate K in the order (dy, channel chunk, dx).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -533,8 +545,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   const float g0 = __uint_as_float(sh << 16), g1 = __uint_as_float(sh & 0xFFFF0000u);
                   const __nv_bfloat162 t2 = __floats2bfloat162_rn(f0 - g0, f1 - g1);
                   const uint32_t sl = *reinterpret_cast<const uint32_t*>(&t2);
-                  f0 = g0 + __uint_as_float(sl << 16);
-                  f1 = g1 + __uint_as_float(sl & 0xFFFF0000u);
+                  // (plain bf16 path: only hi is stored, so the stored value is g)
+                  f0 = p.has_lo_out ? g0 + __uint_as_float(sl << 16) : g0;
+                  f1 = p.has_lo_out ? g1 + __uint_as_float(sl & 0xFFFF0000u) : g1;
                 }
                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
                 hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
