@@ -212,6 +212,8 @@ def main() -> None:
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its banner ("NCCL version ...") to stdout when NCCL_DEBUG >= VERSION: keep stdout = the JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     mnet.set_device(local)
     mnet.set_stream(torch.cuda.current_stream().cuda_stream)
