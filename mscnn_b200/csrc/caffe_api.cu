@@ -6,6 +6,8 @@
 #include "caffe/common.hpp"
 #include "caffe/syncedmem.hpp"
 
+#include "caffe/layer_factory.hpp"
+
 namespace caffe {
 
 // ------------------------------------------------------------------------------- Caffe
@@ -415,5 +417,13 @@ Dtype Blob<Dtype>::sumsq_data() {
 }
 
 INSTANTIATE_CLASS(Blob);
+
+// The one layer-type table of the process (see layer_factory.hpp).
+template <typename Dtype>
+typename LayerRegistry<Dtype>::CreatorRegistry& LayerRegistry<Dtype>::Registry() {
+  static CreatorRegistry* g_registry_ = new CreatorRegistry();
+  return *g_registry_;
+}
+template class LayerRegistry<float>;
 
 }  // namespace caffe

@@ -23,7 +23,7 @@ const int kMaxBlobAxes = 32;
 namespace caffe {
 
 // Device buffer pair for the planes representation (grow-only, like Blob::Reshape).
-struct PlaneStore {
+struct CAFFE_API PlaneStore {
   void* hi = nullptr;
   void* lo = nullptr;
   size_t capacity = 0;     // bytes per plane
@@ -33,7 +33,7 @@ struct PlaneStore {
 };
 
 template <typename Dtype>
-class Blob {
+class CAFFE_API Blob {
  public:
   Blob() : data_(), count_(0), capacity_(0), layout_head_(HEAD_NCHW), planes_split_(false), version_(0) {}
   explicit Blob(const int num, const int channels, const int height, const int width);

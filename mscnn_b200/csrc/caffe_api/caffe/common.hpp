@@ -27,6 +27,14 @@
 #include "caffe/logging.hpp"
 #include "mscnn_b200.h"
 
+// libmscnn_b200.so is built with hidden visibility; the Caffe-API mirror is its exported C++ surface, so that a C++
+// host that includes these headers links against the library like it would against libcaffe.so.
+#if defined(__GNUC__)
+#define CAFFE_API __attribute__((visibility("default")))
+#else
+#define CAFFE_API
+#endif
+
 #define DISABLE_COPY_AND_ASSIGN(classname) \
  private:                                  \
   classname(const classname&);             \
@@ -61,7 +69,7 @@ using std::set;
 using std::string;
 using std::vector;
 
-class Caffe {
+class CAFFE_API Caffe {
  public:
   enum Brew { CPU, GPU };
   enum Precision { FP32_SPLIT, BF16 };

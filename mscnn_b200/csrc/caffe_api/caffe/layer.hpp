@@ -19,7 +19,7 @@
 namespace caffe {
 
 template <typename Dtype>
-class Layer {
+class CAFFE_API Layer {
  public:
   explicit Layer(const LayerParameter& param) : layer_param_(param) {
     phase_ = param.phase();

@@ -14,15 +14,14 @@ template <typename Dtype>
 class Layer;
 
 template <typename Dtype>
-class LayerRegistry {
+class CAFFE_API LayerRegistry {
  public:
   typedef shared_ptr<Layer<Dtype> > (*Creator)(const LayerParameter&);
   typedef std::map<string, Creator> CreatorRegistry;
 
-  static CreatorRegistry& Registry() {
-    static CreatorRegistry* g_registry_ = new CreatorRegistry();
-    return *g_registry_;
-  }
+  // Defined once, inside the library (caffe_api.cu): layers registered by the host program and the library's own
+  // layers must meet in ONE table (an inline function-local static would exist once per binary).
+  static CreatorRegistry& Registry();
   static void AddCreator(const string& type, Creator creator) {
     CreatorRegistry& registry = Registry();
     CHECK_EQ(registry.count(type), 0) << "Layer type " << type << " already registered.";
@@ -52,7 +51,7 @@ class LayerRegistry {
 };
 
 template <typename Dtype>
-class LayerRegisterer {
+class CAFFE_API LayerRegisterer {
  public:
   LayerRegisterer(const string& type, shared_ptr<Layer<Dtype> > (*creator)(const LayerParameter&)) {
     LayerRegistry<Dtype>::AddCreator(type, creator);

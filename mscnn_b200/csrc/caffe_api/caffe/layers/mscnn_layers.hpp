@@ -15,7 +15,7 @@ namespace caffe {
 
 // Fill a parameter blob according to a FillerParameter (include/caffe/filler.hpp).  Supported:
 // constant, gaussian, bilinear (the only ones the MS-CNN prototxts name); anything else aborts.
-void FillBlob(const FillerParameter& filler, Blob<float>* blob);
+CAFFE_API void FillBlob(const FillerParameter& filler, Blob<float>* blob);
 
 // Device copies of packed weights (planes) owned by Convolution / InnerProduct layers.
 struct PackedParam {
@@ -30,7 +30,7 @@ struct PackedParam {
 
 /// InputLayer: /root/reference/src/caffe/layers/input_layer.cpp:8-22
 template <typename Dtype>
-class InputLayer : public Layer<Dtype> {
+class CAFFE_API InputLayer : public Layer<Dtype> {
  public:
   explicit InputLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -47,7 +47,7 @@ template <typename Dtype> class PoolingLayer;
 /// ConvolutionLayer: conv_layer.cpp:8-40 / base_conv_layer.cpp:15-254 (stride 1, group 1, dilation 1:
 /// every Convolution in the shipped deploy nets).  blobs_[0] = [Cout, Cin, kh, kw], blobs_[1] = [Cout].
 template <typename Dtype>
-class ConvolutionLayer : public Layer<Dtype> {
+class CAFFE_API ConvolutionLayer : public Layer<Dtype> {
  public:
   explicit ConvolutionLayer(const LayerParameter& param) : Layer<Dtype>(param), fuse_relu_(false) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -83,7 +83,7 @@ class ConvolutionLayer : public Layer<Dtype> {
 /// DeconvolutionLayer: deconv_layer.cpp:8-40, restricted to the depthwise 4/2/1 bilinear-upsampling
 /// shape of the "-2x" nets.
 template <typename Dtype>
-class DeconvolutionLayer : public Layer<Dtype> {
+class CAFFE_API DeconvolutionLayer : public Layer<Dtype> {
  public:
   explicit DeconvolutionLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -98,7 +98,7 @@ class DeconvolutionLayer : public Layer<Dtype> {
 
 /// ReLULayer: relu_layer.cpp:9-19 (negative_slope 0), in place.
 template <typename Dtype>
-class ReLULayer : public Layer<Dtype> {
+class CAFFE_API ReLULayer : public Layer<Dtype> {
  public:
   explicit ReLULayer(const LayerParameter& param) : Layer<Dtype>(param), fused_(false) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -117,7 +117,7 @@ class ReLULayer : public Layer<Dtype> {
 
 /// PoolingLayer: pooling_layer.cpp:16-220 (MAX / AVE, pad 0, ceil-mode output size).
 template <typename Dtype>
-class PoolingLayer : public Layer<Dtype> {
+class CAFFE_API PoolingLayer : public Layer<Dtype> {
  public:
   explicit PoolingLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -138,7 +138,7 @@ class PoolingLayer : public Layer<Dtype> {
 
 /// SplitLayer: split_layer.cpp:9-31 (forward = share data).
 template <typename Dtype>
-class SplitLayer : public Layer<Dtype> {
+class CAFFE_API SplitLayer : public Layer<Dtype> {
  public:
   explicit SplitLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -151,7 +151,7 @@ class SplitLayer : public Layer<Dtype> {
 
 /// ConcatLayer: concat_layer.cpp:11-74, channel axis.
 template <typename Dtype>
-class ConcatLayer : public Layer<Dtype> {
+class CAFFE_API ConcatLayer : public Layer<Dtype> {
  public:
   explicit ConcatLayer(const LayerParameter& param) : Layer<Dtype>(param), fused_(false) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -169,7 +169,7 @@ class ConcatLayer : public Layer<Dtype> {
 /// InnerProductLayer: inner_product_layer.cpp:10-97 (axis 1, no transpose).
 /// blobs_[0] = [N_out, K] with K in the bottom's NCHW flattening, blobs_[1] = [N_out].
 template <typename Dtype>
-class InnerProductLayer : public Layer<Dtype> {
+class CAFFE_API InnerProductLayer : public Layer<Dtype> {
  public:
   explicit InnerProductLayer(const LayerParameter& param) : Layer<Dtype>(param), fuse_relu_(false) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -187,7 +187,7 @@ class InnerProductLayer : public Layer<Dtype> {
 
 /// DropoutLayer: dropout_layer.cpp:31-46 -- TEST phase is the identity.
 template <typename Dtype>
-class DropoutLayer : public Layer<Dtype> {
+class CAFFE_API DropoutLayer : public Layer<Dtype> {
  public:
   explicit DropoutLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
@@ -204,7 +204,7 @@ class DropoutLayer : public Layer<Dtype> {
 /// Unlike the reference (CPU only) this runs on the device; one small D2H copy of the row count
 /// is needed because the Caffe API exposes R as the blobs' shape.
 template <typename Dtype>
-class BoxOutputLayer : public Layer<Dtype> {
+class CAFFE_API BoxOutputLayer : public Layer<Dtype> {
  public:
   explicit BoxOutputLayer(const LayerParameter& param)
       : Layer<Dtype>(param), workspace_(nullptr), workspace_bytes_(0), num_out_dev_(nullptr),
@@ -234,7 +234,7 @@ class BoxOutputLayer : public Layer<Dtype> {
 
 /// ROIPoolingLayer: roi_pooling_layer.cpp:22-139 with the MS-CNN pad_ratio extension.
 template <typename Dtype>
-class ROIPoolingLayer : public Layer<Dtype> {
+class CAFFE_API ROIPoolingLayer : public Layer<Dtype> {
  public:
   explicit ROIPoolingLayer(const LayerParameter& param)
       : Layer<Dtype>(param), concat_top_(nullptr), concat_offset_(0), concat_channels_(0) {}
@@ -276,7 +276,7 @@ class ROIPoolingLayer : public Layer<Dtype> {
 
 /// ROIAlignLayer: roi_align_layer.cpp:22-139 (cascade WIDER-face net).  top = [R, C, pooled_h+1, pooled_w+1].
 template <typename Dtype>
-class ROIAlignLayer : public Layer<Dtype> {
+class CAFFE_API ROIAlignLayer : public Layer<Dtype> {
  public:
   explicit ROIAlignLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -295,7 +295,7 @@ class ROIAlignLayer : public Layer<Dtype> {
 /// DecodeBBoxLayer: decode_bbox_layer.cpp:17-124, TEST phase (2 bottoms: bbox_pred [R,8], prior ROIs [R,5]).
 /// CPU-only in the reference; here it stays on the device, so the cascade stages do not sync with the host.
 template <typename Dtype>
-class DecodeBBoxLayer : public Layer<Dtype> {
+class CAFFE_API DecodeBBoxLayer : public Layer<Dtype> {
  public:
   explicit DecodeBBoxLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -311,7 +311,7 @@ class DecodeBBoxLayer : public Layer<Dtype> {
 
 /// SoftmaxLayer: softmax_layer.cpp:10-62.
 template <typename Dtype>
-class SoftmaxLayer : public Layer<Dtype> {
+class CAFFE_API SoftmaxLayer : public Layer<Dtype> {
  public:
   explicit SoftmaxLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
@@ -325,7 +325,7 @@ class SoftmaxLayer : public Layer<Dtype> {
 
 /// EltwiseLayer: eltwise_layer.cpp:10-96 (PROD / SUM with coefficients / MAX).
 template <typename Dtype>
-class EltwiseLayer : public Layer<Dtype> {
+class CAFFE_API EltwiseLayer : public Layer<Dtype> {
  public:
   explicit EltwiseLayer(const LayerParameter& param) : Layer<Dtype>(param) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);

@@ -22,12 +22,12 @@
 
 namespace caffe {
 
-void InsertSplits(const NetParameter& param, NetParameter* param_split);
+CAFFE_API void InsertSplits(const NetParameter& param, NetParameter* param_split);
 // text-format NetParameter from a string (throws std::runtime_error on syntax errors)
-void proto_text_read_string(const char* text, NetParameter* param);
+CAFFE_API void proto_text_read_string(const char* text, NetParameter* param);
 
 template <typename Dtype>
-class Net {
+class CAFFE_API Net {
  public:
   explicit Net(const NetParameter& param);
   explicit Net(const string& param_file, Phase phase);

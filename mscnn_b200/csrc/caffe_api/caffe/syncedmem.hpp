@@ -8,7 +8,7 @@
 
 namespace caffe {
 
-class SyncedMemory {
+class CAFFE_API SyncedMemory {
  public:
   SyncedMemory() : cpu_ptr_(NULL), gpu_ptr_(NULL), size_(0), head_(UNINITIALIZED), own_cpu_data_(false),
                    own_gpu_data_(false) {}
