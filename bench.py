@@ -213,6 +213,9 @@ def main() -> None:
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its banner ("NCCL version ...") to stdout when NCCL_DEBUG >= VERSION: keep stdout = the JSON line
+        # (NCCL honours NCCL_DEBUG_FILE only above the VERSION level, so VERSION is raised to WARN)
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     mnet.set_device(local)
