@@ -11,6 +11,7 @@ Outputs (committed):
   layers.npz           single-layer known-answer vectors for BoxOutput / ROIPooling edge cases.
   e2e_cascade_kitti_96x320.npz   cascade-mscnn-7s-576-2x geometry, 2x3x96x320: per-stage proposals, class
                        probabilities, decoded boxes (`python tests/golden/make_golden.py cascade`).
+  e2e_wider_128x192.npz  WIDER FACE mscnn-12s-2x geometry, 2x3x128x192 (main_wider).
   e2e_cascade_wider_128x192.npz  cascade-mscnn-12s-align geometry (ROIAlign, shared heads, Eltwise), 2x3x128x192.
   layers_cascade.npz   single-layer vectors for ROIAlign / DecodeBBox / Softmax / Eltwise edge cases.
 """
@@ -95,6 +96,20 @@ layer { bottom: "x" bottom: "r" top: "c" name: "c" type: "ROIPooling" roi_poolin
     print("layers.npz:", {k: v.shape for k, v in vec.items()})
 
 
+WIDER_HEADS = [f"LFCN_1_{z}x{z}" for z in (12, 16, 24, 32, 48)] + [f"LFCN_2_{z}x{z}" for z in (64, 96)] + \
+    [f"LFCN_3_{z}x{z}" for z in (128, 192)] + [f"LFCN_4_{z}x{z}" for z in (256, 384, 480)]
+
+
+def main_wider():
+    """e2e_wider_128x192.npz: WIDER FACE mscnn-12s-2x geometry (twelve 1x1 heads of 6 channels, AVE pool6, bbox
+    normalisation in BoxOutput, 5x5 ROI pooling on conv4_3_2x, fc6 2048), 2x3x128x192 (BASELINE.json configs[4])."""
+    g = run_net(models.widerface(128, 192, batch=2), 2, 128, 192,
+                keep=WIDER_HEADS + ["proposals", "proposals_score", "cls_pred", "bbox_pred"],
+                sub=["conv4_3", "conv4_3_2x", "conv5_3", "pool6", "roi_pool", "fc6"])
+    np.savez_compressed(OUT / "e2e_wider_128x192.npz", **g)
+    print("e2e_wider_128x192: proposals", g["proposals"].shape)
+
+
 def main_cascade():
     stages = ["proposals", "proposals_2nd", "proposals_3rd", "output_bbox_1st", "output_bbox_2nd", "output_bbox_3rd",
               "cls_prob_1st", "cls_prob_2nd", "cls_prob_3rd", "cls_pred", "cls_pred_2nd", "cls_pred_3rd",
@@ -159,6 +174,9 @@ layer { name: "em" type: "Eltwise" bottom: "s" bottom: "sm" bottom: "d1" top: "e
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cascade":
         main_cascade()
+    elif len(sys.argv) > 1 and sys.argv[1] == "wider":
+        main_wider()
     else:
         main()
+        main_wider()
         main_cascade()
