@@ -11,6 +11,7 @@ Outputs (committed):
   layers.npz           single-layer known-answer vectors for BoxOutput / ROIPooling edge cases.
   e2e_cascade_kitti_96x320.npz   cascade-mscnn-7s-576-2x geometry, 2x3x96x320: per-stage proposals, class
                        probabilities, decoded boxes (`python tests/golden/make_golden.py cascade`).
+  e2e_8s_192x640.npz   mscnn-8s-768 geometry (the bench architecture), 2x3x192x640 (main_8s).
   e2e_wider_128x192.npz  WIDER FACE mscnn-12s-2x geometry, 2x3x128x192 (main_wider).
   e2e_cascade_wider_128x192.npz  cascade-mscnn-12s-align geometry (ROIAlign, shared heads, Eltwise), 2x3x128x192.
   layers_cascade.npz   single-layer vectors for ROIAlign / DecodeBBox / Softmax / Eltwise edge cases.
@@ -100,6 +101,16 @@ WIDER_HEADS = [f"LFCN_1_{z}x{z}" for z in (12, 16, 24, 32, 48)] + [f"LFCN_2_{z}x
     [f"LFCN_3_{z}x{z}" for z in (128, 192)] + [f"LFCN_4_{z}x{z}" for z in (256, 384, 480)]
 
 
+def main_8s():
+    """e2e_8s_192x640.npz: the bench architecture (mscnn-8s-768: eight heads, the last pair on pool6) at 2x3x192x640."""
+    heads8 = [f"LFCN_{i}_{k}x{k}" for i in (1, 2, 3, 4) for k in (5, 7)]
+    g = run_net(models.kitti(192, 640, 8, False, batch=2), 2, 192, 640,
+                keep=heads8 + ["proposals", "proposals_score", "cls_pred", "bbox_pred"],
+                sub=["conv1_2", "conv2_2", "conv3_3", "conv4_3", "conv5_3", "conv6_1", "roi_pool", "fc6"])
+    np.savez_compressed(OUT / "e2e_8s_192x640.npz", **g)
+    print("e2e_8s_192x640: proposals", g["proposals"].shape)
+
+
 def main_wider():
     """e2e_wider_128x192.npz: WIDER FACE mscnn-12s-2x geometry (twelve 1x1 heads of 6 channels, AVE pool6, bbox
     normalisation in BoxOutput, 5x5 ROI pooling on conv4_3_2x, fc6 2048), 2x3x128x192 (BASELINE.json configs[4])."""
@@ -176,7 +187,10 @@ if __name__ == "__main__":
         main_cascade()
     elif len(sys.argv) > 1 and sys.argv[1] == "wider":
         main_wider()
+    elif len(sys.argv) > 1 and sys.argv[1] == "8s":
+        main_8s()
     else:
         main()
+        main_8s()
         main_wider()
         main_cascade()

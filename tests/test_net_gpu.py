@@ -369,6 +369,40 @@ def test_cascade_final_detections_vs_oracle(cuda):
             start += n_i
 
 
+def test_e2e_kitti_8s_vs_reference(cuda):
+    """The bench architecture itself (mscnn-8s-768: eight heads, the last pair on pool6) at 2x3x192x640, default net
+    configuration (pooling fused into conv1_2 / conv2_2 / conv3_3, so those three blobs are never materialised)."""
+    from mscnn_b200 import models
+    g = np.load(GOLD / "e2e_8s_192x640.npz")
+    net = _build(models.kitti(192, 640, 8, False, batch=2), 2, 192, 640, "fp32")
+    out = net.forward()
+    for b in ["conv4_3", "conv5_3", "conv6_1"]:
+        x = net.blob(b)
+        assert tuple(g[b + "__shape"]) == x.shape
+        sub, ref, m2 = x.reshape(-1)[::SUB], g[b + "__sub"], float(g[b + "__m2"][0])
+        assert _rel_ok(sub, ref, 1e-3, m2).mean() >= 0.999, b
+    heads = [k for k in g.files if k.startswith("LFCN_")]
+    assert len(heads) == 8
+    for b in heads:
+        x, ref = net.blob(b), g[b]
+        m2 = float(np.mean(ref.astype(np.float64) ** 2))
+        assert _rel_ok(x, ref, 1e-3, m2).mean() >= 0.999, b
+    ref_ps = g["proposals_score"].reshape(-1, 6)
+    got_ps = out["proposals_score"].reshape(-1, 6)
+    assert abs(len(got_ps) - len(ref_ps)) <= max(2, 0.01 * len(ref_ps))
+    frac = _match_rows(got_ps, ref_ps, 1e-3)
+    assert frac >= 0.98, f"only {frac:.4f} of the reference proposals matched"
+    k = min(len(got_ps), len(ref_ps))
+    ext = np.maximum(np.maximum(ref_ps[:k, 3] - ref_ps[:k, 1], ref_ps[:k, 4] - ref_ps[:k, 2]), 1.0)
+    same = (np.abs(got_ps[:k, 1:5] - ref_ps[:k, 1:5]).max(axis=1) <= 1e-3 * ext) & (got_ps[:k, 0] == ref_ps[:k, 0])
+    assert same.mean() > 0.5
+    for name in ("cls_pred", "bbox_pred"):
+        a, r = out[name].reshape(len(got_ps), -1)[:k][same], g[name].reshape(len(ref_ps), -1)[:k][same]
+        m2 = float(np.mean(r.astype(np.float64) ** 2))
+        assert _rel_ok(a, r, 1e-3, m2).mean() >= 0.99, name
+    print(f"[8s] proposals {len(got_ps)} vs {len(ref_ps)}, matched {frac:.4f}, aligned prefix {same.mean():.3f}")
+
+
 def test_e2e_widerface_vs_reference(cuda):
     """WIDER FACE mscnn-12s-2x geometry (BASELINE.json configs[4]): twelve 1x1 heads of 6 channels, AVE pool6, bbox
     normalisation inside BoxOutput, Deconvolution 2x, 5x5 ROI pooling, fc6 2048 -- against the reference's own CPU
