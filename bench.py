@@ -375,6 +375,7 @@ def main() -> None:
         "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": r["ms_e2e"] / args.steps,
                 "h2d_bytes_per_step": B * 3 * NET_H * NET_W * 4 * world,
                 "d2h_bytes_per_step": (B * cap * 5 * 4 + B * 4) * world,
+                "pipelined": True,   # the upload inside step k is step k+1's batch; serial_* below is the strict order
                 "serial_value": total_images / (r["ms_e2e_serial"] / 1e3),
                 "serial_ms_per_step": r["ms_e2e_serial"] / args.steps,
                 "api": "mscnn_b200.net.Net: forward_only / detect / set_input_async(pinned host, next step's batch, "
