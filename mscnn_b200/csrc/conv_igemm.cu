@@ -71,6 +71,9 @@ struct IgemmParams {
   int a_taps;         // two-ring engine: 3 = one activation slot serves the three dx taps (row shifts), 1 = one slot per tap
   int b_split;        // two-ring engine, BLOCK_N = 256: a weight slot holds ONE tile; B_hi and B_lo of a tap follow each other
   int b_slot;         // bytes per weight slot
+  int pair;           // two-ring engine on CTA PAIRS (cluster of 2, tcgen05 cta_group::2): the pair computes two adjacent M
+                      // tiles of one n tile with MMAs of M = 256; each CTA loads its own activation tile and HALF of
+                      // every weight tile, the leader (cluster rank 0) issues the MMAs for both (tools/umma_2cta_probe.cu)
   int acc_sets;       // TMEM accumulator sets: 2 (epilogue of tile i overlaps the MMAs of tile i + 1) or, when two wide
                       // sub-tiles of BLOCK_N = 128 already fill the 512 columns, 1 (vpool mode only)
   int vpool;          // row-share mode over image-row PAIRS (mt = 2: sub-tile j = row 2 th + j) with the 2x2 MAX pooling
@@ -138,6 +141,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = p.pair ? ptx::cluster_ctarank() : 0u;  // position in the CTA pair
+  const bool leader = (rank == 0u);
 
   if (threadIdx.x == 0) {
     ptx::prefetch_tmap(&tmA_hi);
@@ -160,22 +165,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), kEpiThreads);
+      ptx::mbar_init(tempty_bar(a), kEpiThreads * (p.pair ? 2 : 1));  // pair: both CTAs' epilogues release the leader
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(sTmemPtr, static_cast<uint32_t>(p.tmem_cols));
-    ptx::tmem_relinquish();
+    if (p.pair) {
+      ptx::tmem_alloc_2sm(sTmemPtr, static_cast<uint32_t>(p.tmem_cols));
+      ptx::tmem_relinquish_2sm();
+    } else {
+      ptx::tmem_alloc(sTmemPtr, static_cast<uint32_t>(p.tmem_cols));
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (p.pair) ptx::cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   // the host guarantees m_tiles % MT == 0; in vpool mode the tile grid is already one of row pairs
-  const int total_tiles = p.vpool ? m_tiles * p.n_tiles : (m_tiles / MT) * p.n_tiles;
+  const int total_tiles = p.pair ? ((m_tiles + 1) / 2) * p.n_tiles
+                          : p.vpool ? m_tiles * p.n_tiles : (m_tiles / MT) * p.n_tiles;
+  // pair mode: `tile` counts PAIR tiles, a cluster strides over them; this CTA's M tile is 2 * (tile / n_tiles) + rank
+  // (an odd tile count leaves a phantom M tile: its loads are zero-filled and its stores clipped by TMA)
+  const int tile_first = p.pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = p.pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_kb = (p.fat ? 1 : p.num_terms) * p.taps_h * p.taps_w * p.cin_chunks;
   const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * kBlockK * 2;
   const uint32_t stage_tx = (p.fat ? 2u : 1u) * (static_cast<uint32_t>(MT) * a_box_bytes + kBBytes);
@@ -201,10 +217,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       const bool single = (p.num_terms == 1);  // plain bf16 path: no lo planes anywhere
       const uint32_t a_tx = (single ? 1u : 2u) * static_cast<uint32_t>((p.box_w + halo) * p.box_h * p.box_n * (p.vpool ? 2 : 1)) * kBlockK * 2;
       const uint32_t b_tx = (p.b_split || single) ? kBBytes : 2u * kBBytes;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int n_tile = tile % p.n_tiles;
         int tw, th, tn;
-        m_coords(tile / p.n_tiles, tw, th, tn);
+        m_coords(p.pair ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles, tw, th, tn);
         const int wa = tw * p.box_w - p.pad_w, ha = th * (p.vpool ? 2 : p.box_h) - p.pad_h, na = tn * p.box_n;
         for (int dy = 0; dy < p.taps_h; ++dy) {
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
@@ -212,11 +228,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
               if (p.a_taps == 1 || dx == 0) {
                 ptx::mbar_wait(empty_bar(sa), pa ^ 1u);
                 if (ptx::elect_one()) {
-                  ptx::mbar_expect_tx(full_bar(sa), a_tx);
                   const uint32_t a0 = sA + sa * p.a_slot;
                   const int wx = wa + (p.a_taps == 1 ? dx : 0);
-                  ptx::tma_load_4d(a0, &tmA_hi, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
-                  if (!single) ptx::tma_load_4d(a0 + p.a_slot / 2, &tmA_lo, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
+                  if (p.pair) {
+                    // both CTAs' tiles are counted on the LEADER's barrier, which alone expects the bytes of both
+                    const uint32_t lb = ptx::mapa(full_bar(sa), 0);
+                    if (leader) ptx::mbar_expect_tx(full_bar(sa), 2u * a_tx);
+                    ptx::tma_load_4d_2sm(a0, &tmA_hi, lb, cc * kBlockK, wx, ha + dy, na);
+                    ptx::tma_load_4d_2sm(a0 + p.a_slot / 2, &tmA_lo, lb, cc * kBlockK, wx, ha + dy, na);
+                  } else {
+                    ptx::mbar_expect_tx(full_bar(sa), a_tx);
+                    ptx::tma_load_4d(a0, &tmA_hi, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
+                    if (!single) ptx::tma_load_4d(a0 + p.a_slot / 2, &tmA_lo, full_bar(sa), cc * kBlockK, wx, ha + dy, na);
+                  }
                 }
                 __syncwarp();
                 if (++sa == p.sa_slots) { sa = 0; pa ^= 1u; }
@@ -226,11 +250,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                 const int bi = p.sa_slots + sb;
                 ptx::mbar_wait(empty_bar(bi), pb ^ 1u);
                 if (ptx::elect_one()) {
-                  ptx::mbar_expect_tx(full_bar(bi), b_tx);
                   const uint32_t b0 = sB + sb * p.b_slot;
-                  if (p.b_split) {
+                  if (p.pair) {
+                    // this CTA's half of the weight tile: output columns [128 rank, 128 rank + 128) of the n tile
+                    if (leader) ptx::mbar_expect_tx(full_bar(bi), kBBytes);
+                    ptx::tma_load_2d_2sm(b0, half == 0 ? &tmB_hi : &tmB_lo, ptx::mapa(full_bar(bi), 0), kcol,
+                                         n_tile * BLOCK_N + static_cast<int>(rank) * (BLOCK_N / 2));
+                  } else if (p.b_split) {
+                    ptx::mbar_expect_tx(full_bar(bi), b_tx);
                     ptx::tma_load_2d(b0, half == 0 ? &tmB_hi : &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
                   } else {
+                    ptx::mbar_expect_tx(full_bar(bi), b_tx);
                     ptx::tma_load_2d(b0, &tmB_hi, full_bar(bi), kcol, n_tile * BLOCK_N);
                     if (!single) ptx::tma_load_2d(b0 + kBBytes, &tmB_lo, full_bar(bi), kcol, n_tile * BLOCK_N);
                   }
@@ -245,7 +275,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     }
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles && !p.rowshare; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles && !p.rowshare; tile += tile_step) {
       const int n_tile = tile % p.n_tiles, m0 = (tile / p.n_tiles) * MT;
       int w0[kMaxMt], h0[kMaxMt], n0[kMaxMt];
 #pragma unroll
@@ -300,11 +330,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (p.rowshare) {
+    if (p.rowshare && (leader || !p.pair)) {  // pair mode: the leader issues the MMAs of both CTAs
+      constexpr uint32_t kIdescPair = ptx::umma_idesc_bf16(2 * kBlockM, BLOCK_N);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+        if (p.pair) ptx::mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);  // arrivals come from both CTAs
+        else ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t acc_w = static_cast<uint32_t>(p.wide ? 2 * BLOCK_N : BLOCK_N);
         const uint32_t d_base = tmem_base + static_cast<uint32_t>(acc * MT) * acc_w;
@@ -334,6 +366,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   if (ptx::elect_one()) {
                     const uint64_t b_desc = ptx::umma_desc_sw128(sB + sb * p.b_slot);
                     const uint64_t ah = ptx::umma_desc_sw128(a_hi + shift), al = ptx::umma_desc_sw128(a_lo + shift);
+                    if (p.pair) {
+                      // M = 256 across the pair: A = each CTA's own 128 rows, B = the two half tiles side by side
+                      if (half == 0) {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                          ptx::umma_bf16_2sm(d_base, al + 2u * k, b_desc + 2u * k, kIdescPair, (first | k) != 0 ? 1u : 0u);
+                          ptx::umma_bf16_2sm(d_base, ah + 2u * k, b_desc + 2u * k, kIdescPair, 1u);
+                        }
+                      } else {
+#pragma unroll
+                        for (int k = 0; k < kBlockK / 16; ++k)
+                          ptx::umma_bf16_2sm(d_base, ah + 2u * k, b_desc + 2u * k, kIdescPair, 1u);
+                      }
+                      ptx::umma_commit_2sm(empty_bar(bi));  // frees the slot in BOTH CTAs
+                      if (half == 1 && a_done) ptx::umma_commit_2sm(empty_bar(sa_now));
+                      if (half == 1 && last) ptx::umma_commit_2sm(tfull_bar(acc));
+                    } else {
                     if (half == 0) {
 #pragma unroll
                       for (int k = 0; k < kBlockK / 16; ++k) {
@@ -347,6 +396,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                     ptx::umma_commit(empty_bar(bi));
                     if (half == 1 && a_done) ptx::umma_commit(empty_bar(sa_now));
                     if (half == 1 && last) ptx::umma_commit(tfull_bar(acc));
+                    }
                   }
                   __syncwarp();
                   first = 1u;
@@ -403,7 +453,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         if (acc == 0) acc_phase ^= 1u;
       }
     }
-    for (int tile = blockIdx.x; tile < total_tiles && !p.rowshare; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles && !p.rowshare; tile += tile_step) {
       ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       ptx::tc_fence_after();
       const uint32_t acc_w = static_cast<uint32_t>(p.wide ? 2 * BLOCK_N : BLOCK_N);  // TMEM columns per sub-tile
@@ -470,8 +520,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     uint32_t acc_phase = 0;
     int ebuf = 0;
     const int hw_box = p.box_w * p.box_h;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles, m0 = (tile / p.n_tiles) * MT;
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
+      const int n_tile = tile % p.n_tiles;
+      const int m0 = p.pair ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : (tile / p.n_tiles) * MT;
       const int n_base = n_tile * BLOCK_N;
       // bias slice for this n tile (visible after the first named barrier below)
       for (int j = et; j < BLOCK_N; j += kEpiThreads) bias_s[j] = p.bias[n_base + j];
@@ -764,9 +815,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       }
       if (p.out_mode != MSCNN_OUT_NHWC_BF16)
         ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // bias_s reuse hazard for the next tile
-      // all TMEM reads of these accumulators are done -> hand them back to the MMA warp
+      // all TMEM reads of these accumulators are done -> hand them back to the MMA warp (pair mode: the leader's)
       ptx::tc_fence_before();
-      ptx::mbar_arrive(tempty_bar(acc));
+      if (p.pair && !leader) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(acc), 0));
+      else ptx::mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -774,10 +826,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (p.pair) ptx::cluster_sync_all();  // the peer may still be arriving on this CTA's barriers / reading its weights
+  else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if (p.pair) ptx::tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    else ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 }
 
@@ -827,6 +881,30 @@ static cudaError_t launch_igemm(const CUtensorMap maps[8], const IgemmParams& p,
   mscnn::note_launch();
   kern<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
   return cudaGetLastError();
+}
+
+// CTA-pair launch: cluster dimension (2, 1, 1) as a launch attribute (the kernel itself serves both modes).
+static cudaError_t launch_igemm_pair(const CUtensorMap maps[8], const IgemmParams& p, int grid, size_t smem,
+                                     cudaStream_t stream) {
+  auto kern = conv_igemm_kernel<256>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2;
+  attr.val.clusterDim.y = 1;
+  attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = 1;
+  mscnn::note_launch();
+  e = cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 }  // namespace mscnn
@@ -988,12 +1066,14 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (split && BN == 256 && !getenv("MSCNN_NO_RING256")) {
     const bool halo = (d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !getenv("MSCNN_NO_ROWSHARE"));
     const int a_plane = halo ? ((p.box_w + 2) * 128 + 1023) / 1024 * 1024 : kABytes;
-    const int a_slot = 2 * a_plane, b_slot = b_bytes;
+    // CTA pairs (opt-in, MSCNN_2CTA=1): half weight tiles per CTA, MMAs of M = 256 issued by the leader
+    p.pair = (getenv("MSCNN_2CTA") && d->out_mode == MSCNN_OUT_NHWC_BF16 && !pool && mscnn_sm_count() >= 2) ? 1 : 0;
+    const int a_slot = 2 * a_plane, b_slot = p.pair ? b_bytes / 2 : b_bytes;
     const int eb = (epi_unit == 0) ? 0 : 1;
     const int rings = budget - misc - eb * epi_unit;
     for (int sa = 3; sa >= 2 && !p.rowshare; --sa) {
       int sb = (rings - sa * a_slot) / b_slot;
-      if (sb > 4) sb = 4;
+      if (sb > (p.pair ? 5 : 4)) sb = p.pair ? 5 : 4;
       if (sb >= 3) {
         p.rowshare = 1;
         p.a_taps = halo ? 3 : 1;
@@ -1008,6 +1088,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
         smem_rs = (size_t)sa * a_slot + (size_t)sb * b_slot + (size_t)eb * epi_unit + misc;
       }
     }
+    if (!p.rowshare) p.pair = 0;
   }
   p.mt = mt;
   int tcols = 32;
@@ -1017,8 +1098,8 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   p.epi_bufs = epi_bufs;  // 0 in fp32-output mode: no staging region is carved
   const size_t smem = p.rowshare ? smem_rs : (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
   if (getenv("MSCNN_VERBOSE_CONV"))
-    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d rowshare=%d(%d+%d) vpool=%d a_taps=%d b_split=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
-            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.vpool, p.a_taps, p.b_split, p.num_terms, stages,
+    fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d rowshare=%d(%d+%d) vpool=%d a_taps=%d b_split=%d pair=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
+            d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.vpool, p.a_taps, p.b_split, p.pair, p.num_terms, stages,
             epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
   CUtensorMap maps[8];
@@ -1035,10 +1116,11 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
     maps[1] = maps[0];
   }
   const uint64_t ktot = (uint64_t)d->KH * d->KW * d->C;
-  rc = tmap_2d_bf16(&maps[2], d->w_hi, ktot, (uint64_t)d->Cout_pad, 64u, (uint32_t)BN);
+  const uint32_t b_box_rows = (uint32_t)(p.pair ? BN / 2 : BN);
+  rc = tmap_2d_bf16(&maps[2], d->w_hi, ktot, (uint64_t)d->Cout_pad, 64u, b_box_rows);
   if (rc) return rc;
   if (split) {
-    rc = tmap_2d_bf16(&maps[3], d->w_lo, ktot, (uint64_t)d->Cout_pad, 64u, (uint32_t)BN);
+    rc = tmap_2d_bf16(&maps[3], d->w_lo, ktot, (uint64_t)d->Cout_pad, 64u, b_box_rows);
     if (rc) return rc;
   } else {
     maps[3] = maps[2];
@@ -1080,9 +1162,14 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
                                   : p.tiles_w * p.tiles_h * p.tiles_n / p.mt * p.n_tiles;
   int grid = mscnn_sm_count();
   if (grid > total_tiles) grid = total_tiles;
+  if (p.pair) {  // whole clusters of two
+    const int pair_tiles = (p.tiles_w * p.tiles_h * p.tiles_n + 1) / 2 * p.n_tiles;
+    grid = mscnn_sm_count() & ~1;
+    if (grid > 2 * pair_tiles) grid = 2 * pair_tiles;
+  }
   cudaError_t e;
   switch (BN) {
-    case 256: e = launch_igemm<256>(maps, p, grid, smem, stream); break;
+    case 256: e = p.pair ? launch_igemm_pair(maps, p, grid, smem, stream) : launch_igemm<256>(maps, p, grid, smem, stream); break;
     case 128: e = launch_igemm<128>(maps, p, grid, smem, stream); break;
     case 64: e = launch_igemm<64>(maps, p, grid, smem, stream); break;
     default: e = launch_igemm<32>(maps, p, grid, smem, stream); break;
