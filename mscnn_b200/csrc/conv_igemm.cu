@@ -95,7 +95,9 @@ constexpr int kEpiThreads = 128;
 constexpr int kEpiBarId = 1;
 constexpr int kMaxMt = 4;
 
-template <int BLOCK_N>
+// PAIR: the CTA-pair (cluster of 2, tcgen05 cta_group::2) build of the two-ring engine.  It is a separate instantiation:
+// a kernel that contains cluster / cta_group::2 instructions can only be launched as a cluster.
+template <int BLOCK_N, bool PAIR = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   const __grid_constant__ CUtensorMap tmA_lo,
@@ -141,7 +143,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = p.pair ? ptx::cluster_ctarank() : 0u;  // position in the CTA pair
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;  // position in the CTA pair
   const bool leader = (rank == 0u);
 
   if (threadIdx.x == 0) {
@@ -165,12 +167,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(tfull_bar(a), 1);
-      ptx::mbar_init(tempty_bar(a), kEpiThreads * (p.pair ? 2 : 1));  // pair: both CTAs' epilogues release the leader
+      ptx::mbar_init(tempty_bar(a), kEpiThreads * (PAIR ? 2 : 1));  // pair: both CTAs' epilogues release the leader
     }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    if (p.pair) {
+    if (PAIR) {
       ptx::tmem_alloc_2sm(sTmemPtr, static_cast<uint32_t>(p.tmem_cols));
       ptx::tmem_relinquish_2sm();
     } else {
@@ -179,19 +181,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     }
   }
   ptx::tc_fence_before();
-  if (p.pair) ptx::cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
+  if (PAIR) ptx::cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
   // the host guarantees m_tiles % MT == 0; in vpool mode the tile grid is already one of row pairs
-  const int total_tiles = p.pair ? ((m_tiles + 1) / 2) * p.n_tiles
+  const int total_tiles = PAIR ? ((m_tiles + 1) / 2) * p.n_tiles
                           : p.vpool ? m_tiles * p.n_tiles : (m_tiles / MT) * p.n_tiles;
   // pair mode: `tile` counts PAIR tiles, a cluster strides over them; this CTA's M tile is 2 * (tile / n_tiles) + rank
   // (an odd tile count leaves a phantom M tile: its loads are zero-filled and its stores clipped by TMA)
-  const int tile_first = p.pair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-  const int tile_step = p.pair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int tile_first = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int num_kb = (p.fat ? 1 : p.num_terms) * p.taps_h * p.taps_w * p.cin_chunks;
   const uint32_t a_box_bytes = static_cast<uint32_t>(p.box_w * p.box_h * p.box_n) * kBlockK * 2;
   const uint32_t stage_tx = (p.fat ? 2u : 1u) * (static_cast<uint32_t>(MT) * a_box_bytes + kBBytes);
@@ -220,7 +222,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int n_tile = tile % p.n_tiles;
         int tw, th, tn;
-        m_coords(p.pair ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles, tw, th, tn);
+        m_coords(PAIR ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : tile / p.n_tiles, tw, th, tn);
         const int wa = tw * p.box_w - p.pad_w, ha = th * (p.vpool ? 2 : p.box_h) - p.pad_h, na = tn * p.box_n;
         for (int dy = 0; dy < p.taps_h; ++dy) {
           for (int cc = 0; cc < p.cin_chunks; ++cc) {
@@ -230,7 +232,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                 if (ptx::elect_one()) {
                   const uint32_t a0 = sA + sa * p.a_slot;
                   const int wx = wa + (p.a_taps == 1 ? dx : 0);
-                  if (p.pair) {
+                  if (PAIR) {
                     // both CTAs' tiles are counted on the LEADER's barrier, which alone expects the bytes of both
                     const uint32_t lb = ptx::mapa(full_bar(sa), 0);
                     if (leader) ptx::mbar_expect_tx(full_bar(sa), 2u * a_tx);
@@ -251,7 +253,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                 ptx::mbar_wait(empty_bar(bi), pb ^ 1u);
                 if (ptx::elect_one()) {
                   const uint32_t b0 = sB + sb * p.b_slot;
-                  if (p.pair) {
+                  if (PAIR) {
                     // this CTA's half of the weight tile: output columns [128 rank, 128 rank + 128) of the n tile
                     if (leader) ptx::mbar_expect_tx(full_bar(bi), kBBytes);
                     ptx::tma_load_2d_2sm(b0, half == 0 ? &tmB_hi : &tmB_lo, ptx::mapa(full_bar(bi), 0), kcol,
@@ -330,12 +332,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (p.rowshare && (leader || !p.pair)) {  // pair mode: the leader issues the MMAs of both CTAs
+    if (p.rowshare && (leader || !PAIR)) {  // pair mode: the leader issues the MMAs of both CTAs
       constexpr uint32_t kIdescPair = ptx::umma_idesc_bf16(2 * kBlockM, BLOCK_N);
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-        if (p.pair) ptx::mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);  // arrivals come from both CTAs
+        if (PAIR) ptx::mbar_wait_cluster(tempty_bar(acc), acc_phase ^ 1u);  // arrivals come from both CTAs
         else ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         ptx::tc_fence_after();
         const uint32_t acc_w = static_cast<uint32_t>(p.wide ? 2 * BLOCK_N : BLOCK_N);
@@ -366,7 +368,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
                   if (ptx::elect_one()) {
                     const uint64_t b_desc = ptx::umma_desc_sw128(sB + sb * p.b_slot);
                     const uint64_t ah = ptx::umma_desc_sw128(a_hi + shift), al = ptx::umma_desc_sw128(a_lo + shift);
-                    if (p.pair) {
+                    if (PAIR) {
                       // M = 256 across the pair: A = each CTA's own 128 rows, B = the two half tiles side by side
                       if (half == 0) {
 #pragma unroll
@@ -522,7 +524,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
     const int hw_box = p.box_w * p.box_h;
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int n_tile = tile % p.n_tiles;
-      const int m0 = p.pair ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : (tile / p.n_tiles) * MT;
+      const int m0 = PAIR ? 2 * (tile / p.n_tiles) + static_cast<int>(rank) : (tile / p.n_tiles) * MT;
       const int n_base = n_tile * BLOCK_N;
       // bias slice for this n tile (visible after the first named barrier below)
       for (int j = et; j < BLOCK_N; j += kEpiThreads) bias_s[j] = p.bias[n_base + j];
@@ -817,7 +819,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
         ptx::named_bar_sync(kEpiBarId, kEpiThreads);  // bias_s reuse hazard for the next tile
       // all TMEM reads of these accumulators are done -> hand them back to the MMA warp (pair mode: the leader's)
       ptx::tc_fence_before();
-      if (p.pair && !leader) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(acc), 0));
+      if (PAIR && !leader) ptx::mbar_arrive_cluster(ptx::mapa(tempty_bar(acc), 0));
       else ptx::mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -826,11 +828,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   }
 
   ptx::tc_fence_before();
-  if (p.pair) ptx::cluster_sync_all();  // the peer may still be arriving on this CTA's barriers / reading its weights
+  if (PAIR) ptx::cluster_sync_all();  // the peer may still be arriving on this CTA's barriers / reading its weights
   else __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    if (p.pair) ptx::tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
+    if (PAIR) ptx::tmem_dealloc_2sm(tmem_base, static_cast<uint32_t>(p.tmem_cols));
     else ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(p.tmem_cols));
   }
 }
@@ -875,7 +877,7 @@ static void pick_box(int N, int Ho, int Wo, bool even, int* bw_o, int* bh_o, int
 template <int BLOCK_N>
 static cudaError_t launch_igemm(const CUtensorMap maps[8], const IgemmParams& p, int grid,
                                 size_t smem, cudaStream_t stream) {
-  auto kern = conv_igemm_kernel<BLOCK_N>;
+  auto kern = conv_igemm_kernel<BLOCK_N, false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   mscnn::note_launch();
@@ -886,7 +888,7 @@ static cudaError_t launch_igemm(const CUtensorMap maps[8], const IgemmParams& p,
 // CTA-pair launch: cluster dimension (2, 1, 1) as a launch attribute (the kernel itself serves both modes).
 static cudaError_t launch_igemm_pair(const CUtensorMap maps[8], const IgemmParams& p, int grid, size_t smem,
                                      cudaStream_t stream) {
-  auto kern = conv_igemm_kernel<256>;
+  auto kern = conv_igemm_kernel<256, true>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
