@@ -33,6 +33,8 @@
 //         slots, B_hi -> lo*hi + hi*hi, B_lo -> hi*lo;
 //       - "vpool": tiles of two image rows x 128 pixels whose 2x2 max pooling happens in registers (vertical: the
 //         two accumulators, horizontal: lane ^ 1), bit-identical to conv -> store -> pool_kernel.
+//       - CTA pairs (PAIR instantiation, BLOCK_N = 256): clusters of two CTAs, tcgen05 cta_group::2 MMAs of M = 256
+//         issued by the leader; every SM loads and reads only half of each weight tile.
 //     All paths accumulate K in the order (dy, channel chunk, dx).
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -1068,8 +1070,9 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (split && BN == 256 && !getenv("MSCNN_NO_RING256")) {
     const bool halo = (d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !getenv("MSCNN_NO_ROWSHARE"));
     const int a_plane = halo ? ((p.box_w + 2) * 128 + 1023) / 1024 * 1024 : kABytes;
-    // CTA pairs (opt-in, MSCNN_2CTA=1): half weight tiles per CTA, MMAs of M = 256 issued by the leader
-    p.pair = (getenv("MSCNN_2CTA") && d->out_mode == MSCNN_OUT_NHWC_BF16 && !pool && mscnn_sm_count() >= 2) ? 1 : 0;
+    // CTA pairs (MSCNN_NO_2CTA=1 turns them off): half weight tiles per CTA, MMAs of M = 256 issued by the leader;
+    // conv3_2 2.13 -> 2.00 ms, the step 37.3 -> 35.5 ms on the same B200 (profiles/r01n_summary.md)
+    p.pair = (!getenv("MSCNN_NO_2CTA") && d->out_mode == MSCNN_OUT_NHWC_BF16 && !pool && mscnn_sm_count() >= 2) ? 1 : 0;
     const int a_slot = 2 * a_plane, b_slot = p.pair ? b_bytes / 2 : b_bytes;
     const int eb = (epi_unit == 0) ? 0 : 1;
     const int rings = budget - misc - eb * epi_unit;
