@@ -31,6 +31,26 @@ def test_library_carries_sm100a_tensor_core_code():
     assert "UTCHMMA" in out and "UTMALDG" in out and "UTMASTG" in out and "LDTM" in out
 
 
+def test_only_the_pair_kernel_contains_cluster_instructions():
+    """A kernel that contains cta_group::2 / cluster instructions can only be launched as a cluster ("cluster
+    misconfiguration" otherwise): the CTA-pair build of the convolution kernel must be its own instantiation, and it
+    must really carry the 2-CTA tensor-core instructions."""
+    out = subprocess.run(["cuobjdump", "-sass", str(ROOT / "mscnn_b200" / "libmscnn_b200.so")],
+                         capture_output=True, text=True).stdout
+    if not out:
+        pytest.skip("cuobjdump unavailable")
+    users, fn = {}, None
+    for line in out.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            fn = m.group(1)
+        elif fn and re.search(r"\b(UTCHMMA\.2CTA|UTCATOMSWS\.2CTA|UCGABAR_ARV|UCGABAR_WAIT)", line):
+            users[fn] = users.get(fn, 0) + 1
+    assert users, "no 2-CTA instructions in the library: the CTA-pair kernel is missing"
+    assert all("conv_igemm_kernelILi256ELb1" in f for f in users), sorted(users)
+    assert any("UTCHMMA.2CTA" in l for l in out.splitlines())
+
+
 def test_net_kitti_8s_structure():
     from mscnn_b200 import models
     from mscnn_b200.net import Net
