@@ -418,12 +418,44 @@ Dtype Blob<Dtype>::sumsq_data() {
 
 INSTANTIATE_CLASS(Blob);
 
-// The one layer-type table of the process (see layer_factory.hpp).
+// The one layer-type table of the process and its accessors (layer_factory.hpp).
 template <typename Dtype>
 typename LayerRegistry<Dtype>::CreatorRegistry& LayerRegistry<Dtype>::Registry() {
-  static CreatorRegistry* g_registry_ = new CreatorRegistry();
-  return *g_registry_;
+  static CreatorRegistry* table = new CreatorRegistry();  // never destroyed: layers may be created during shutdown
+  return *table;
 }
+
+template <typename Dtype>
+void LayerRegistry<Dtype>::AddCreator(const string& type, Creator creator) {
+  const bool fresh = Registry().insert(std::make_pair(type, creator)).second;
+  CHECK(fresh) << "Layer type " << type << " already registered.";
+}
+
+template <typename Dtype>
+vector<string> LayerRegistry<Dtype>::LayerTypeList() {
+  vector<string> names;
+  for (const auto& entry : Registry()) names.push_back(entry.first);
+  return names;
+}
+
+template <typename Dtype>
+shared_ptr<Layer<Dtype> > LayerRegistry<Dtype>::CreateLayer(const LayerParameter& param) {
+  const CreatorRegistry& table = Registry();
+  const typename CreatorRegistry::const_iterator it = table.find(param.type());
+  if (it == table.end()) {
+    string known;
+    for (const string& t : LayerTypeList()) known += (known.empty() ? "" : ", ") + t;
+    LOG(FATAL) << "Unknown layer type: " << param.type() << " (known types: " << known << ")";
+  }
+  return it->second(param);
+}
+
+template <typename Dtype>
+LayerRegisterer<Dtype>::LayerRegisterer(const string& type, typename LayerRegistry<Dtype>::Creator creator) {
+  LayerRegistry<Dtype>::AddCreator(type, creator);
+}
+
 template class LayerRegistry<float>;
+template struct LayerRegisterer<float>;
 
 }  // namespace caffe

@@ -1,5 +1,10 @@
-// LayerRegistry / REGISTER_LAYER_CLASS -- same interface as
-// /root/reference/include/caffe/layer_factory.hpp:56-137 (type string -> creator).
+// Layer-type registry with the interface of /root/reference/include/caffe/layer_factory.hpp:56-137: a type string maps
+// to a creator function; REGISTER_LAYER_CLASS / REGISTER_LAYER_CREATOR add entries at static-initialisation time and
+// Net::Init asks CreateLayer for every LayerParameter.
+//
+// Unlike the reference (header-only, one table per binary that instantiates it), the table and its accessors live
+// INSIDE libmscnn_b200.so (caffe_api.cu) and are exported: layer types registered by a host program and the library's
+// own layers meet in one table (examples/caffe_driver.cpp registers "HostPass").
 #pragma once
 #include <map>
 #include <string>
@@ -19,53 +24,34 @@ class CAFFE_API LayerRegistry {
   typedef shared_ptr<Layer<Dtype> > (*Creator)(const LayerParameter&);
   typedef std::map<string, Creator> CreatorRegistry;
 
-  // Defined once, inside the library (caffe_api.cu): layers registered by the host program and the library's own
-  // layers must meet in ONE table (an inline function-local static would exist once per binary).
   static CreatorRegistry& Registry();
-  static void AddCreator(const string& type, Creator creator) {
-    CreatorRegistry& registry = Registry();
-    CHECK_EQ(registry.count(type), 0) << "Layer type " << type << " already registered.";
-    registry[type] = creator;
-  }
-  static shared_ptr<Layer<Dtype> > CreateLayer(const LayerParameter& param) {
-    const string& type = param.type();
-    CreatorRegistry& registry = Registry();
-    CHECK_EQ(registry.count(type), 1) << "Unknown layer type: " << type
-                                      << " (known types: " << LayerTypeListString() << ")";
-    return registry[type](param);
-  }
-  static vector<string> LayerTypeList() {
-    vector<string> layer_types;
-    for (typename CreatorRegistry::iterator it = Registry().begin(); it != Registry().end(); ++it)
-      layer_types.push_back(it->first);
-    return layer_types;
-  }
+  static void AddCreator(const string& type, Creator creator);                  // aborts on a duplicate type
+  static shared_ptr<Layer<Dtype> > CreateLayer(const LayerParameter& param);    // aborts on an unknown type
+  static vector<string> LayerTypeList();
 
  private:
-  LayerRegistry() {}
-  static string LayerTypeListString() {
-    string s;
-    for (const string& t : LayerTypeList()) s += (s.empty() ? "" : ", ") + t;
-    return s;
-  }
+  LayerRegistry();  // static interface only
 };
 
+// Registers a creator from its constructor (one static object per registered type).
 template <typename Dtype>
-class CAFFE_API LayerRegisterer {
- public:
-  LayerRegisterer(const string& type, shared_ptr<Layer<Dtype> > (*creator)(const LayerParameter&)) {
-    LayerRegistry<Dtype>::AddCreator(type, creator);
-  }
+struct CAFFE_API LayerRegisterer {
+  LayerRegisterer(const string& type, typename LayerRegistry<Dtype>::Creator creator);
 };
 
-#define REGISTER_LAYER_CREATOR(type, creator) \
-  static LayerRegisterer<float> g_creator_f_##type(#type, creator<float>)
+namespace detail {
+// creator of a class template `SomeLayer<Dtype>` with the usual (const LayerParameter&) constructor
+template <template <typename> class LayerT, typename Dtype>
+shared_ptr<Layer<Dtype> > make_layer(const LayerParameter& param) {
+  return shared_ptr<Layer<Dtype> >(new LayerT<Dtype>(param));
+}
+}  // namespace detail
 
-#define REGISTER_LAYER_CLASS(type)                                              \
-  template <typename Dtype>                                                     \
-  shared_ptr<Layer<Dtype> > Creator_##type##Layer(const LayerParameter& param) { \
-    return shared_ptr<Layer<Dtype> >(new type##Layer<Dtype>(param));            \
-  }                                                                             \
-  REGISTER_LAYER_CREATOR(type, Creator_##type##Layer)
+// mscnn_b200 instantiates float only (see INSTANTIATE_CLASS in common.hpp).
+#define REGISTER_LAYER_CREATOR(type, creator) \
+  static ::caffe::LayerRegisterer<float> g_creator_f_##type(#type, creator<float>)
+
+#define REGISTER_LAYER_CLASS(type) \
+  static ::caffe::LayerRegisterer<float> g_creator_f_##type(#type, &::caffe::detail::make_layer<type##Layer, float>)
 
 }  // namespace caffe
