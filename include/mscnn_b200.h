@@ -63,6 +63,10 @@ MSCNN_API const char* mscnn_version(void);
 MSCNN_API int mscnn_sm_count(void);
 /* Number of CUDA kernels this library has launched in this process so far (all entry points). */
 MSCNN_API unsigned long long mscnn_kernel_launch_count(void);
+/* The MSCNN_* environment switches are read once, not per launch.  This re-reads them and drops the
+ * cached convolution launch plans; mscnn_net_create calls it.  The reference reads its switches (Caffe::mode, cuDNN
+ * engine choice) at layer set-up too (src/caffe/layer_factory.cpp:37-65). */
+MSCNN_API void mscnn_config_reload(void);
 
 /* ------------------------------------------------------------------------------------
  * Convolution (stride 1) / InnerProduct with fused bias and optional ReLU.

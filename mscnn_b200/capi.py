@@ -96,6 +96,8 @@ def _declare(L: C.CDLL) -> None:
     L.mscnn_sm_count.restype = c_int
     L.mscnn_kernel_launch_count.restype = C.c_ulonglong
     L.mscnn_kernel_launch_count.argtypes = []
+    L.mscnn_config_reload.restype = None
+    L.mscnn_config_reload.argtypes = []
     L.mscnn_conv_forward.restype = c_int
     L.mscnn_conv_forward.argtypes = [C.POINTER(ConvDesc), c_void_p]
     L.mscnn_pack_conv_weights.restype = c_int

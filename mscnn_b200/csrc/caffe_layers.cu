@@ -5,6 +5,7 @@
 #include <string>
 
 #include "caffe/layers/mscnn_layers.hpp"
+#include "config.h"
 
 namespace caffe {
 
@@ -162,7 +163,7 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
   // taps move into the GEMM's N dimension and a 1-D gather sums them (mscnn_head_gather in the C ABI).
   const bool head_path = (num_output_ == 9 || num_output_ == 6) && kernel_h_ == kernel_w_ && kernel_h_ > 1 &&
                          pad_h_ == pad_w_ && 2 * pad_h_ + 1 == kernel_h_ && !fuse_relu_ && channels_ % 64 == 0 &&
-                         !std::getenv("MSCNN_NO_HEAD_TAPS");
+                         !mscnn::config().no_head_taps;
   if (head_path) {
     const int k = kernel_h_;
     const int n_pad = (k * num_output_ + 63) / 64 * 64;
@@ -206,7 +207,7 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
   // conv1_1-style layer (3 input channels, 3x3, pad 1): K = 27 is far below one 64-channel
   // tensor-core k-block; it runs as a direct exact-fp32 kernel straight from the NCHW input blob.
   const bool first_path = (channels_ == 3 && kernel_h_ == 3 && kernel_w_ == 3 && pad_h_ == 1 && pad_w_ == 1);
-  const char* conv1_mode = std::getenv("MSCNN_CONV1");  // "pair" | "direct" | "patch" | default = single tensor-core kernel
+  const int conv1_mode = mscnn::config().conv1_mode;  // MSCNN_CONV1: 1 "pair" | 2 "direct" | 3 "patch" | 0 default = single tensor-core kernel
   if (first_path && num_output_ == 64 && !conv1_mode) {
     // One kernel from the fp32 NCHW blob to planes: pixel rows staged once, the horizontal taps are
     // descriptor-shifted views of them (mscnn_conv1_tc_forward, conv_c3_tc.cu).
@@ -235,7 +236,7 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
                                        N, H, W, fuse_relu_ ? 1 : 0, Caffe::stream()));
     return;
   }
-  if (first_path && (W % 2 == 0) && num_output_ % 64 == 0 && conv1_mode && std::string(conv1_mode) == "pair") {
+  if (first_path && (W % 2 == 0) && num_output_ % 64 == 0 && conv1_mode == 1) {
     // Pixel-pair GEMM: rows = two adjacent pixels (K = 54 of 64), block-diagonal weights, the output
     // [N][H][W/2][2*Cout] is the NHWC tensor [N][H][W][Cout] (see mscnn_im2col3x3_c3_pair_to_planes).
     const int cp = num_output_;  // multiple of 64
@@ -283,7 +284,7 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
     MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
     return;
   }
-  if (first_path && !(conv1_mode && std::string(conv1_mode) == "patch")) {
+  if (first_path && conv1_mode != 3) {
     typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
     MSCNN_CHECK(mscnn_conv3x3_c3_forward(bottom[0]->gpu_data(), this->blobs_[0]->gpu_data(),
                                          bias ? bias->gpu_data() : nullptr, y.hi, y.lo, N, H, W, num_output_,

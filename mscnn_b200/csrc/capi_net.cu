@@ -62,6 +62,7 @@ int mscnn_set_device(int device) {
 }
 
 void* mscnn_net_create(const char* prototxt, int is_path) {
+  mscnn_config_reload();  // the MSCNN_* switches are read when a net is created (and never per launch)
   Caffe::set_mode(Caffe::GPU);
   NetHandle* h = new NetHandle();
   if (is_path) {

@@ -1,0 +1,19 @@
+// Process-wide switches of the library, read from the environment ONCE (first use) instead of with getenv() on every
+// launch.  mscnn_config_reload() re-reads them and drops every cached launch plan: it exists for the tests, which hold
+// each operand-delivery variant of the convolution kernel to the others bit for bit.
+#pragma once
+
+namespace mscnn {
+
+struct Config {
+  bool no_fat, no_wide, no_rowshare, no_vpool, no_ring256, no_2cta, no_bf16_rings;
+  bool no_head_taps, no_fusion, no_pool_fusion, no_roi_fuse, no_graph;
+  bool verbose_conv, c3_swap;
+  int mt;          // MSCNN_MT, 0 = per-layer default
+  int conv1_mode;  // MSCNN_CONV1: 0 = tensor-core kernel (default), 1 = pair, 2 = direct, 3 = patch
+  unsigned epoch;  // bumped by every reload: cached plans carry the epoch they were built under
+};
+
+const Config& config();
+
+}  // namespace mscnn

@@ -28,6 +28,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "config.h"
 #include "mscnn_b200.h"
 #include "ptx_sm100.cuh"
 #include "tmap.h"
@@ -352,7 +353,7 @@ extern "C" int mscnn_conv1_tc_forward(const float* x, const void* packed_w, cons
   p.tiles_w = (W + c3::kTileW - 1) / c3::kTileW;
   p.split = y_lo ? 1 : 0;
   p.relu = relu ? 1 : 0;
-  p.swap = getenv("MSCNN_C3_SWAP") ? 1 : 0;
+  p.swap = mscnn::config().c3_swap ? 1 : 0;
   CUtensorMap maps[2];
   memset(maps, 0, sizeof(maps));
   const uint64_t odim[4] = {64u, (uint64_t)W, (uint64_t)H, (uint64_t)N};

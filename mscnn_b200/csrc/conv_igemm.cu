@@ -44,6 +44,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
+#include "config.h"
 #include "mscnn_b200.h"
 #include "ptx_sm100.cuh"
 #include "tmap.h"
@@ -876,11 +880,24 @@ static void pick_box(int N, int Ho, int Wo, bool even, int* bw_o, int* bh_o, int
   *bn_o = b_n;
 }
 
+constexpr int kSmemBudget = 227 * 1024;
+constexpr int kMaxDevices = 64;
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per device and function: raised once to the whole budget.
+template <typename K>
+static cudaError_t raise_smem_once(K kern, bool (&done)[kMaxDevices], int device) {
+  if (device >= 0 && device < kMaxDevices && done[device]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+  if (e == cudaSuccess && device >= 0 && device < kMaxDevices) done[device] = true;
+  return e;
+}
+
 template <int BLOCK_N>
 static cudaError_t launch_igemm(const CUtensorMap maps[8], const IgemmParams& p, int grid,
-                                size_t smem, cudaStream_t stream) {
+                                size_t smem, int device, cudaStream_t stream) {
   auto kern = conv_igemm_kernel<BLOCK_N, false>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static bool done[kMaxDevices];
+  cudaError_t e = raise_smem_once(kern, done, device);
   if (e != cudaSuccess) return e;
   mscnn::note_launch();
   kern<<<grid, kThreads, smem, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], p);
@@ -889,9 +906,10 @@ static cudaError_t launch_igemm(const CUtensorMap maps[8], const IgemmParams& p,
 
 // CTA-pair launch: cluster dimension (2, 1, 1) as a launch attribute (the kernel itself serves both modes).
 static cudaError_t launch_igemm_pair(const CUtensorMap maps[8], const IgemmParams& p, int grid, size_t smem,
-                                     cudaStream_t stream) {
+                                     int device, cudaStream_t stream) {
   auto kern = conv_igemm_kernel<256, true>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static bool done[kMaxDevices];
+  cudaError_t e = raise_smem_once(kern, done, device);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
@@ -911,13 +929,94 @@ static cudaError_t launch_igemm_pair(const CUtensorMap maps[8], const IgemmParam
   return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+// A launch plan: everything mscnn_conv_forward derives from a descriptor (tile shapes, ring sizes, the eight tensor
+// maps).  Plans are cached per (descriptor, device, config epoch): a steady-state forward does one hash lookup per
+// convolution instead of ~15 getenv() and up to 8 cuTensorMapEncodeTiled calls (27 convolutions per step).
+struct ConvPlan {
+  IgemmParams p;
+  CUtensorMap maps[8];
+  int grid;
+  int BN;
+  size_t smem;
+};
+
+struct PlanKey {
+  const void* ptr[10];
+  int v[15];
+  bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
+};
+struct PlanKeyHash {
+  size_t operator()(const PlanKey& k) const {
+    const unsigned char* b = reinterpret_cast<const unsigned char*>(&k);
+    uint64_t h = 1469598103934665603ull;  // FNV-1a
+    for (size_t i = 0; i < sizeof(PlanKey); ++i) h = (h ^ b[i]) * 1099511628211ull;
+    return static_cast<size_t>(h);
+  }
+};
+static std::mutex g_plan_mu;
+static std::unordered_map<PlanKey, ConvPlan, PlanKeyHash> g_plans;
+
+void conv_plan_cache_clear() {
+  std::lock_guard<std::mutex> lk(g_plan_mu);
+  g_plans.clear();
+}
+
+static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan);
+
 }  // namespace mscnn
 
 using namespace mscnn;
 
 extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
-  if (!d || !d->x_hi || !d->w_hi || !d->bias) return MSCNN_ERR_INVALID;
+  if (!d) return MSCNN_ERR_INVALID;
+  int device = 0;
+  if (cudaGetDevice(&device) != cudaSuccess) return MSCNN_ERR_CUDA;
+  PlanKey key;
+  memset(&key, 0, sizeof(key));
+  const void* ptrs[10] = {d->x_hi, d->x_lo, d->w_hi, d->w_lo, d->bias, d->y_hi, d->y_lo, d->y_f32, d->pool_hi, d->pool_lo};
+  memcpy(key.ptr, ptrs, sizeof(ptrs));
+  const int vals[15] = {d->N, d->H, d->W, d->C, d->Cout, d->Cout_pad, d->KH, d->KW, d->pad_h, d->pad_w, d->relu,
+                        d->out_mode, device, static_cast<int>(config().epoch), 0};
+  memcpy(key.v, vals, sizeof(vals));
+  ConvPlan plan;
+  bool hit = false;
+  {
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) {
+      plan = it->second;
+      hit = true;
+    }
+  }
+  if (!hit) {
+    const int rc = build_plan(d, &plan);
+    if (rc != MSCNN_OK) return rc;
+    std::lock_guard<std::mutex> lk(g_plan_mu);
+    if (g_plans.size() >= 4096) g_plans.clear();  // blobs that keep moving (re-allocation): bound the table
+    g_plans.emplace(key, plan);
+  }
+  cudaError_t e;
+  const IgemmParams& p = plan.p;
+  switch (plan.BN) {
+    case 256: e = p.pair ? launch_igemm_pair(plan.maps, p, plan.grid, plan.smem, device, stream)
+                         : launch_igemm<256>(plan.maps, p, plan.grid, plan.smem, device, stream); break;
+    case 128: e = launch_igemm<128>(plan.maps, p, plan.grid, plan.smem, device, stream); break;
+    case 64: e = launch_igemm<64>(plan.maps, p, plan.grid, plan.smem, device, stream); break;
+    default: e = launch_igemm<32>(plan.maps, p, plan.grid, plan.smem, device, stream); break;
+  }
+  if (e != cudaSuccess) {
+    fprintf(stderr, "mscnn_conv_forward: launch failed: %s\n", cudaGetErrorString(e));
+    return MSCNN_ERR_CUDA;
+  }
+  return MSCNN_OK;
+}
+
+namespace mscnn {
+
+static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan) {
+  const Config& cfg = config();
+  if (!d->x_hi || !d->w_hi || !d->bias) return MSCNN_ERR_INVALID;
   if (d->C % 64 != 0) return MSCNN_ERR_INVALID;
   const bool split = (d->x_lo != nullptr);
   if (split && !d->w_lo) return MSCNN_ERR_INVALID;
@@ -931,7 +1030,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (pool && ((Ho & 1) || (Wo & 1))) return MSCNN_ERR_INVALID;  // fused pooling: even output extents only
   if ((d->out_mode == MSCNN_OUT_NCHW_F32 || d->out_mode == MSCNN_OUT_NHWC_F32) && !d->y_f32) return MSCNN_ERR_INVALID;
 
-  IgemmParams p;
+  IgemmParams& p = plan->p;
   memset(&p, 0, sizeof(p));
   p.num_terms = split ? 3 : 1;
   p.taps_h = d->KH;
@@ -943,8 +1042,8 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   // Pooled narrow-N 3x3 layers of the fp32-faithful path (conv1_2, conv2_2): row-share mode over image-row pairs
   // with the pooling done in registers (p.vpool, see the kernel).  Tiles are 128 pixels x 2 rows.
   const bool vpair = pool && !d->y_hi && BN <= 128 && d->KW == 3 && d->KH == 3 && (Wo % 128 == 0) &&
-                     !getenv("MSCNN_NO_FAT") && !getenv("MSCNN_NO_ROWSHARE") && !getenv("MSCNN_NO_VPOOL") &&
-                     (split || !getenv("MSCNN_NO_BF16_RINGS"));
+                     !cfg.no_fat && !cfg.no_rowshare && !cfg.no_vpool &&
+                     (split || !cfg.no_bf16_rings);
   if (vpair) {
     p.box_w = 128;
     p.box_h = 1;
@@ -974,8 +1073,8 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   // fat stages (A_hi, A_lo, B_hi, B_lo of a k-block in one stage, three MMAs per K step) for the
   // narrow-N layers of the fp32-faithful path: A_hi / B_hi are fetched once instead of twice and a
   // barrier round trip covers 3x the MMAs (conv1_2: 6.3 -> 3.9 ms, profiles/r01_probe_layers*.log).
-  p.fat = (split && BN <= 128 && !getenv("MSCNN_NO_FAT")) ? 1 : 0;
-  p.wide = (p.fat && !getenv("MSCNN_NO_WIDE")) ? 1 : 0;
+  p.fat = (split && BN <= 128 && !cfg.no_fat) ? 1 : 0;
+  p.wide = (p.fat && !cfg.no_wide) ? 1 : 0;
   // vpair with BN = 128: two wide sub-tiles are 512 TMEM columns, so a single accumulator set (the epilogue of a
   // tile is ~7 % of its MMA time there); keeps the accumulation order of the un-pooled row-share path bit for bit
   p.acc_sets = (vpair && BN == 128 && p.wide) ? 1 : 2;
@@ -986,13 +1085,13 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   int mt = 1;
   if (BN <= 64) mt = 4;
   else if (BN == 128) mt = 2;
-  if (const char* e = getenv("MSCNN_MT")) mt = atoi(e);
+  if (cfg.mt > 0) mt = cfg.mt;
   if (mt > kMaxMt) mt = kMaxMt;
   if (mt < 1) mt = 1;
   while (mt > 1 && (2 * mt * BN * acc_mul > 512 || m_tiles_total % mt != 0 || m_tiles_total / mt * p.n_tiles < mscnn_sm_count())) mt >>= 1;
   const int epi_unit = (d->out_mode == MSCNN_OUT_NHWC_BF16) ? (kABytes + (pool ? kABytes / 4 : 0)) * (p.has_lo_out ? 2 : 1) : 0;
   const int misc = BN * 4 + 8 * (2 * 8 + 4) + 16 + 1024 /*alignment slack*/;
-  const int budget = 227 * 1024;
+  const int budget = kSmemBudget;
   int epi_bufs = (epi_unit == 0) ? 0 : 2;
   int stage_bytes = 0, stages = 0;
   for (;; mt >>= 1) {
@@ -1036,9 +1135,9 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
     }
     if (!p.rowshare) return MSCNN_ERR_INVALID;
   }
-  const bool bf16_rings = !split && !getenv("MSCNN_NO_BF16_RINGS");  // plain bf16: same engine, single planes
+  const bool bf16_rings = !split && !cfg.no_bf16_rings;  // plain bf16: same engine, single planes
   if (!vpair && (p.wide || bf16_rings) && d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool &&
-      !getenv("MSCNN_NO_ROWSHARE")) {
+      !cfg.no_rowshare) {
     const int a_plane = ((p.box_w + 2) * 128 + 1023) / 1024 * 1024;
     const int a_slot = (split ? 2 : 1) * a_plane, b_slot = (split ? 2 : 1) * b_bytes;
     for (int eb = (epi_unit == 0 ? 0 : 2); eb >= (epi_unit == 0 ? 0 : 1) && !p.rowshare; --eb) {
@@ -1067,12 +1166,12 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   // non-fat path fetches A_hi and B_hi twice per (tap, channel chunk) (144 KB of TMA fills); here the activation pair and
   // both weight tiles are fetched once (96 KB; 76 KB with the row-share halo on 128 x 1 boxes): a third less L2->SM and
   // shared-memory fill traffic on the layers that hold 70 % of the step and run against the power cap.
-  if (split && BN == 256 && !getenv("MSCNN_NO_RING256")) {
-    const bool halo = (d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !getenv("MSCNN_NO_ROWSHARE"));
+  if (split && BN == 256 && !cfg.no_ring256) {
+    const bool halo = (d->KW == 3 && p.box_w == 128 && p.box_h == 1 && p.box_n == 1 && !pool && !cfg.no_rowshare);
     const int a_plane = halo ? ((p.box_w + 2) * 128 + 1023) / 1024 * 1024 : kABytes;
     // CTA pairs (MSCNN_NO_2CTA=1 turns them off): half weight tiles per CTA, MMAs of M = 256 issued by the leader;
     // conv3_2 2.13 -> 2.00 ms, the step 37.3 -> 35.5 ms on the same B200 (profiles/r01n_summary.md)
-    p.pair = (!getenv("MSCNN_NO_2CTA") && d->out_mode == MSCNN_OUT_NHWC_BF16 && !pool && mscnn_sm_count() >= 2) ? 1 : 0;
+    p.pair = (!cfg.no_2cta && d->out_mode == MSCNN_OUT_NHWC_BF16 && !pool && mscnn_sm_count() >= 2) ? 1 : 0;
     const int a_slot = 2 * a_plane, b_slot = p.pair ? b_bytes / 2 : b_bytes;
     const int eb = (epi_unit == 0) ? 0 : 1;
     const int rings = budget - misc - eb * epi_unit;
@@ -1102,13 +1201,13 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   p.stages = stages;
   p.epi_bufs = epi_bufs;  // 0 in fp32-output mode: no staging region is carved
   const size_t smem = p.rowshare ? smem_rs : (size_t)stages * stage_bytes + (size_t)epi_bufs * epi_unit + misc;
-  if (getenv("MSCNN_VERBOSE_CONV"))
+  if (cfg.verbose_conv)
     fprintf(stderr, "conv plan: N=%d H=%d W=%d C=%d Cout_pad=%d k=%dx%d BN=%d box=%dx%dx%d mt=%d fat=%d wide=%d rowshare=%d(%d+%d) vpool=%d a_taps=%d b_split=%d pair=%d terms=%d stages=%d epi_bufs=%d smem=%zu tiles=%d\n",
             d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.vpool, p.a_taps, p.b_split, p.pair, p.num_terms, stages,
             epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
-  CUtensorMap maps[8];
-  memset(maps, 0, sizeof(maps));
+  CUtensorMap* maps = plan->maps;
+  memset(maps, 0, sizeof(plan->maps));
   const uint32_t obox[4] = {64u, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
   const uint32_t abox[4] = {64u, (uint32_t)(p.box_w + (p.a_taps == 3 ? 2 : 0)), (uint32_t)(p.vpool ? 2 : p.box_h), (uint32_t)p.box_n};
   const uint64_t adim[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
@@ -1172,16 +1271,10 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
     grid = mscnn_sm_count() & ~1;
     if (grid > 2 * pair_tiles) grid = 2 * pair_tiles;
   }
-  cudaError_t e;
-  switch (BN) {
-    case 256: e = p.pair ? launch_igemm_pair(maps, p, grid, smem, stream) : launch_igemm<256>(maps, p, grid, smem, stream); break;
-    case 128: e = launch_igemm<128>(maps, p, grid, smem, stream); break;
-    case 64: e = launch_igemm<64>(maps, p, grid, smem, stream); break;
-    default: e = launch_igemm<32>(maps, p, grid, smem, stream); break;
-  }
-  if (e != cudaSuccess) {
-    fprintf(stderr, "mscnn_conv_forward: launch failed: %s\n", cudaGetErrorString(e));
-    return MSCNN_ERR_CUDA;
-  }
+  plan->grid = grid;
+  plan->BN = BN;
+  plan->smem = smem;
   return MSCNN_OK;
 }
+
+}  // namespace mscnn

@@ -15,16 +15,22 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// grid: (ceil(W/32), H, N * ceil(Cpad/64)); block 256 = 8 warps.
+// grid: ceil(W/32) * H * N * ceil(Cpad/64) blocks (linear); block 256 = 8 warps.
 // read:  x[n][c][h][w0..w0+31]  (lanes along w, warps along c)       -> coalesced 128 B
 // write: hi[n][h][w][c0..c0+63] (lanes along c pairs, warps along w) -> coalesced 128 B
 __global__ void nchw_to_planes_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
                                       __nv_bfloat16* __restrict__ lo, int N, int C, int H, int W,
                                       int Cpad) {
   __shared__ float tile[64][33];
-  const int cblocks = Cpad / 64;
-  const int n = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 64;
-  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  // linear block index over (n, c block, h, w block): grid.x only (up to 2^31 - 1 blocks; the fc6 blob of a
+  // full-size batch has R * 64 = 100k+ (n, c block) pairs, more than grid.z or grid.y can hold)
+  const int cblocks = Cpad / 64, wblocks = (W + 31) / 32;
+  unsigned bid = blockIdx.x;
+  const int w0 = static_cast<int>(bid % wblocks) * 32;
+  bid /= wblocks;
+  const int h = static_cast<int>(bid % H);
+  bid /= H;
+  const int n = static_cast<int>(bid / cblocks), c0 = static_cast<int>(bid % cblocks) * 64;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int cc = warp; cc < 64; cc += 8) {
     const int c = c0 + cc, w = w0 + lane;
@@ -50,9 +56,15 @@ __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ hi,
                                       const __nv_bfloat16* __restrict__ lo, float* __restrict__ y,
                                       int N, int C, int H, int W, int Cpad) {
   __shared__ float tile[64][33];
-  const int cblocks = Cpad / 64;
-  const int n = blockIdx.z / cblocks, c0 = (blockIdx.z % cblocks) * 64;
-  const int h = blockIdx.y, w0 = blockIdx.x * 32;
+  // linear block index over (n, c block, h, w block): grid.x only (up to 2^31 - 1 blocks; the fc6 blob of a
+  // full-size batch has R * 64 = 100k+ (n, c block) pairs, more than grid.z or grid.y can hold)
+  const int cblocks = Cpad / 64, wblocks = (W + 31) / 32;
+  unsigned bid = blockIdx.x;
+  const int w0 = static_cast<int>(bid % wblocks) * 32;
+  bid /= wblocks;
+  const int h = static_cast<int>(bid % H);
+  bid /= H;
+  const int n = static_cast<int>(bid / cblocks), c0 = static_cast<int>(bid % cblocks) * 64;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int ww = warp; ww < 32; ww += 8) {
     const int w = w0 + ww;
@@ -295,8 +307,9 @@ extern "C" int mscnn_nchw_f32_to_planes(const float* x, void* hi, void* lo, int 
                                         int W, int Cpad, void* stream) {
   if (!x || !hi || N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad % 64 || Cpad < C)
     return MSCNN_ERR_INVALID;
-  if ((long)N * (Cpad / 64) > 65535 || H > 65535) return MSCNN_ERR_INVALID;
-  dim3 grid((W + 31) / 32, H, N * (Cpad / 64));
+  const long long nblocks = (long long)((W + 31) / 32) * H * N * (Cpad / 64);
+  if (nblocks > 2147483647ll) return MSCNN_ERR_INVALID;
+  const unsigned grid = static_cast<unsigned>(nblocks);
   mscnn::note_launch();
   nchw_to_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       x, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo, N, C, H, W, Cpad);
@@ -307,8 +320,9 @@ extern "C" int mscnn_planes_to_nchw_f32(const void* hi, const void* lo, float* y
                                         int H, int W, int Cpad, void* stream) {
   if (!y || !hi || N <= 0 || C <= 0 || H <= 0 || W <= 0 || Cpad % 64 || Cpad < C)
     return MSCNN_ERR_INVALID;
-  if ((long)N * (Cpad / 64) > 65535 || H > 65535) return MSCNN_ERR_INVALID;
-  dim3 grid((W + 31) / 32, H, N * (Cpad / 64));
+  const long long nblocks = (long long)((W + 31) / 32) * H * N * (Cpad / 64);
+  if (nblocks > 2147483647ll) return MSCNN_ERR_INVALID;
+  const unsigned grid = static_cast<unsigned>(nblocks);
   mscnn::note_launch();
   planes_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)hi, (const __nv_bfloat16*)lo, y, N, C, H, W, Cpad);

@@ -16,6 +16,11 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def reload_config() -> None:
+    """Re-read the MSCNN_* environment switches (they are read once per process / per Net otherwise)."""
+    capi.lib().mscnn_config_reload()
+
+
 def pad64(c: int) -> int:
     return (c + 63) // 64 * 64
 

@@ -15,6 +15,11 @@ Outputs (committed):
   e2e_wider_128x192.npz  WIDER FACE mscnn-12s-2x geometry, 2x3x128x192 (main_wider).
   e2e_cascade_wider_128x192.npz  cascade-mscnn-12s-align geometry (ROIAlign, shared heads, Eltwise), 2x3x128x192.
   layers_cascade.npz   single-layer vectors for ROIAlign / DecodeBBox / Softmax / Eltwise edge cases.
+  e2e_8s_768x2560.npz  mscnn-8s-768 at the BASELINE size (1x3x768x2560, configs[2]/[3]): every trunk blob incl.
+                       conv3_1/3_2/3_3 and the pooled blobs sub-sampled (stride 1999), all eight LFCN maps, proposals,
+                       head outputs (`python tests/golden/make_golden.py full`).
+  e2e_wider_768x1024.npz  WIDER FACE mscnn-12s-2x at 1x3x768x1024 (configs[4]).
+  e2e_7s2x_576x1920.npz   mscnn-7s-576-2x at 1x3x576x1920 (configs[1]).
 """
 import sys
 from pathlib import Path
@@ -30,7 +35,7 @@ OUT = Path(__file__).resolve().parent
 SUB = 7919  # subsample stride (prime)
 
 
-def run_net(proto: str, n: int, h: int, w: int, keep: list[str], sub: list[str]):
+def run_net(proto: str, n: int, h: int, w: int, keep: list[str], sub: list[str], SUB: int = SUB):
     net = ref.RefNet(proto, is_path=False)
     layers = [(nm, t, net.param_shapes(nm)) for nm, t in zip(net.layer_names, net.layer_types)]
     net.set_params(synth.make_weights(layers))
@@ -182,8 +187,44 @@ layer { name: "em" type: "Eltwise" bottom: "s" bottom: "sm" bottom: "d1" top: "e
     print("layers_cascade.npz:", {k: v.shape for k, v in vec.items()})
 
 
+SUB_FULL = 1999
+TRUNK_ALL = ["conv1_1", "conv1_2", "pool1", "conv2_1", "conv2_2", "pool2", "conv3_1", "conv3_2", "conv3_3", "pool3",
+             "conv4_1", "conv4_2", "conv4_3", "pool4", "conv5_1", "conv5_2", "conv5_3", "pool5"]
+
+
+def main_full(which=("8s", "wider", "7s2x")):
+    """Full BASELINE sizes, one image each (one 768x2560 forward of the verbatim reference takes about a minute on
+    8 cores).  Sub-sampling stride 1999 (prime; walks through every position class of every tiling)."""
+    import time
+    if "8s" in which:
+        t = time.time()
+        heads8 = [f"LFCN_{i}_{k}x{k}" for i in (1, 2, 3, 4) for k in (5, 7)]
+        g = run_net(models.kitti(768, 2560, 8, False, batch=1), 1, 768, 2560,
+                    keep=heads8 + ["proposals", "proposals_score", "cls_pred", "bbox_pred"],
+                    sub=TRUNK_ALL + ["conv6_1", "pool6", "loss1_conv1", "roi_pool", "roi_c1", "fc6"], SUB=SUB_FULL)
+        np.savez_compressed(OUT / "e2e_8s_768x2560.npz", **g)
+        print("e2e_8s_768x2560: proposals", g["proposals"].shape, f"{time.time() - t:.0f} s", flush=True)
+    if "wider" in which:
+        t = time.time()
+        g = run_net(models.widerface(768, 1024, batch=1), 1, 768, 1024,
+                    keep=WIDER_HEADS + ["proposals", "proposals_score", "cls_pred", "bbox_pred"],
+                    sub=TRUNK_ALL + ["conv4_3_2x", "pool6", "roi_pool", "roi_c1", "fc6"], SUB=SUB_FULL)
+        np.savez_compressed(OUT / "e2e_wider_768x1024.npz", **g)
+        print("e2e_wider_768x1024: proposals", g["proposals"].shape, f"{time.time() - t:.0f} s", flush=True)
+    if "7s2x" in which:
+        t = time.time()
+        heads7 = ["LFCN_1_5x5", "LFCN_1_7x7", "LFCN_2_5x5", "LFCN_2_7x7", "LFCN_3_5x5", "LFCN_3_7x7", "LFCN_4_5x5"]
+        g = run_net(models.kitti(576, 1920, 7, True, batch=1), 1, 576, 1920,
+                    keep=heads7 + ["proposals", "proposals_score", "cls_pred", "bbox_pred"],
+                    sub=TRUNK_ALL + ["conv6_1", "loss1_conv1", "conv4_3_2x", "roi_pool", "roi_c1", "fc6"], SUB=SUB_FULL)
+        np.savez_compressed(OUT / "e2e_7s2x_576x1920.npz", **g)
+        print("e2e_7s2x_576x1920: proposals", g["proposals"].shape, f"{time.time() - t:.0f} s", flush=True)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "cascade":
+    if len(sys.argv) > 1 and sys.argv[1] == "full":
+        main_full(tuple(sys.argv[2:]) or ("8s", "wider", "7s2x"))
+    elif len(sys.argv) > 1 and sys.argv[1] == "cascade":
         main_cascade()
     elif len(sys.argv) > 1 and sys.argv[1] == "wider":
         main_wider()

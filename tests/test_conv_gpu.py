@@ -58,6 +58,18 @@ CASES = [
     ("rowshare_n64",   1, 64, 6, 256, 64, 3, 1),
     ("rowshare_n128",  2, 128, 5, 384, 128, 3, 1),
     ("rowshare_many",  2, 64, 40, 512, 64, 3, 1),
+    # BLOCK_N = 256 on 128x1 boxes: two-ring engine with the row-share halo (a_taps = 3), single-tile weight slots
+    # (b_split) and, by default, CTA pairs -- the variant conv3_x takes at 768x2560 (conv_igemm.cu "BLOCK_N = 256,
+    # fp32-faithful").  Even / odd M-tile counts (odd: the pair build's phantom M tile), one and two n tiles,
+    # 4 and 8 channel chunks, more pair tiles than clusters.
+    ("ring256_halo",   1, 256, 6, 256, 256, 3, 1),
+    ("ring256_odd",    1, 256, 5, 384, 256, 3, 1),
+    ("ring256_2nt",    2, 256, 5, 640, 512, 3, 1),
+    ("ring256_c512",   1, 512, 3, 384, 512, 3, 1),
+    ("ring256_many",   2, 256, 40, 640, 256, 3, 1),
+    # BLOCK_N = 256 on 2-D boxes (a_taps = 1): conv4_x / conv5_x geometry, odd tile count
+    ("ring256_box2d",  1, 256, 24, 40, 512, 3, 1),
+    ("ring256_box2d_odd", 3, 256, 12, 40, 256, 3, 1),
 ]
 
 
@@ -84,6 +96,53 @@ def test_conv_planes(cuda, case, split):
         ref = _ref_conv(x.bfloat16().float(), wt.bfloat16().float(), b, pad, True)
         rms = float(ref.pow(2).mean().sqrt())
         _report(name, got, ref, 2.0 ** -8, 1e-5 * rms)
+
+
+VARIANT_CASES = [c for c in CASES if c[0].startswith("ring256") or c[0] in ("trunk256", "trunk512_2nt", "rowshare_n128")]
+
+
+@pytest.mark.parametrize("case", VARIANT_CASES, ids=[c[0] for c in VARIANT_CASES])
+def test_conv_variants_bit_identical(cuda, case, monkeypatch):
+    """Operand-delivery variants of one layer.  The two-ring engine accumulates a k-block's three products in the order
+    (lo*hi, hi*hi, hi*lo) per (dy, channel chunk, dx) whether it runs on CTA pairs or single CTAs, with or without the
+    row-share halo: default == MSCNN_NO_2CTA == MSCNN_NO_ROWSHARE bit for bit.  MSCNN_NO_RING256 (BLOCK_N = 256) falls
+    back to the term-major loop (all of hi*hi, then hi*lo, then lo*hi): another summation order, held to fp64 only.
+    Every variant must be within 1e-4 of the fp64 convolution."""
+    from mscnn_b200 import ops
+    name, n, cin, h, w, cout, k, pad = case
+    g = torch.Generator(device="cpu").manual_seed(1707)
+    x = torch.randn((n, cin, h, w), generator=g).to(cuda)
+    wt = (torch.randn((cout, cin, k, k), generator=g) * (2.0 / (cin * k * k)) ** 0.5).to(cuda)
+    b = (torch.randn((cout,), generator=g) * 0.1).to(cuda)
+    xp = ops.nchw_to_planes(x, True)
+    wp = ops.pack_conv_weights(wt, b, True)
+    ref = _ref_conv(x, wt, b, pad, True)
+    rms = float(ref.pow(2).mean().sqrt())
+
+    def run(**env):
+        for kk, v in env.items():
+            monkeypatch.setenv(kk, v)
+        ops.reload_config()
+        try:
+            y = ops.conv_forward(xp, wp, pad, relu=True)
+            got = ops.planes_to_nchw(y)
+            torch.cuda.synchronize()
+            _report(f"{name} {env}", got, ref, 1e-4, 1e-4 * rms)
+            return y.hi.clone(), y.lo.clone()
+        finally:
+            for kk in env:
+                monkeypatch.delenv(kk)
+            ops.reload_config()
+
+    base = run()
+    for env in ({"MSCNN_NO_2CTA": "1"}, {"MSCNN_NO_ROWSHARE": "1"}, {"MSCNN_NO_2CTA": "1", "MSCNN_NO_ROWSHARE": "1"}):
+        other = run(**env)
+        same = torch.equal(base[0], other[0]) and torch.equal(base[1], other[1])
+        if not same:
+            d = (base[0] != other[0]) | (base[1] != other[1])
+            pytest.fail(f"{name}: {env} differs from the default build in {int(d.sum())}/{d.numel()} elements, "
+                        f"first at {d.nonzero()[:4].tolist()}")
+    run(MSCNN_NO_RING256="1")
 
 
 @pytest.mark.parametrize("split", [True, False], ids=["split", "bf16"])

@@ -4,8 +4,9 @@ oracle/_ref, tests/golden/make_golden.py), through the Caffe-API mirror's Net (C
 north_star bar: proposal boxes, class scores and final detections within 1e-3 relative on
 identical synthetic inputs (fp32-faithful path).  Because ranking / NMS / round() are discrete, a
 last-bit difference in a score can swap or evict a box; rows are therefore matched by content and
-the test demands that (a) >= 98 % of the reference rows have a partner within 1e-3 and (b) the
-row counts agree within 1 %.  (Measured on B200: 99.0-99.7 % matched.  The residual is inherent to
+the test demands that (a) >= 99.7 % of the reference rows have a partner within 1e-3, (b) the row counts agree
+within 0.5 %, (c) >= 99 % of the rows pair up IN ORDER (two-pointer alignment that re-synchronises behind an inserted /
+deleted row) and (d) the head outputs of those rows are within 1e-3.  (Measured on B200: 99.9-100 % matched.  The residual is inherent to
 any implementation that is not bit-identical in the conv sums: the split-bf16 products carry a
 2^-18 relative error, which moves an IoU by ~1e-4; with ~4e4 IoU evaluations per image a handful
 land that close to the 0.65 threshold, and each flipped suppression adds or removes a row.)  Stage-isolated tests (BoxOutput, ROIPooling fed with the
@@ -58,7 +59,64 @@ def _match_rows(got, ref, tol):
     return hit / len(ref)
 
 
-@pytest.mark.parametrize("precision,feat_tol,row_tol,min_match", [("fp32", 1e-3, 1e-3, 0.98), ("bf16", 6e-2, 5e-2, 0.5)])
+def _row_same(a, r, tol):
+    ext = max(r[3] - r[1], r[4] - r[2], 1.0)
+    return a[0] == r[0] and np.abs(a[1:5] - r[1:5]).max() <= tol * ext
+
+
+def _align_rows(got, ref, tol, look=16):
+    """Order-preserving alignment of two proposal lists (rows [img x1 y1 x2 y2 ...], per image in descending score
+    order).  A flipped NMS decision inserts or deletes a row and shifts everything behind it, and two scores closer
+    than their error may swap; a two-pointer walk with a short look-ahead re-synchronises after such events.  Returns
+    index arrays (gi, ri) of the rows paired IN ORDER; len(gi) / max(len) is the aligned fraction."""
+    gi, ri = [], []
+    i = j = 0
+    while i < len(got) and j < len(ref):
+        if _row_same(got[i], ref[j], tol):
+            gi.append(i); ri.append(j); i += 1; j += 1
+            continue
+        step = None
+        for d in range(1, look + 1):
+            if i + d < len(got) and _row_same(got[i + d], ref[j], tol):
+                step = (d, 0); break
+            if j + d < len(ref) and _row_same(got[i], ref[j + d], tol):
+                step = (0, d); break
+        if step is None:
+            i += 1; j += 1
+        else:
+            i += step[0]; j += step[1]
+    return np.array(gi, dtype=np.int64), np.array(ri, dtype=np.int64)
+
+
+def _check_rows_and_head(out, g, tol, min_match, min_aligned, min_head, tag):
+    """Proposals row by row and the detection head on the rows aligned in order.  Thresholds are the figures measured
+    on B200 (see the prints), north_star tolerance 1e-3 relative."""
+    ref_ps = g["proposals_score"].reshape(-1, 6)
+    got_ps = out["proposals_score"].reshape(-1, 6)
+    assert abs(len(got_ps) - len(ref_ps)) <= max(2, 0.005 * len(ref_ps)), (len(got_ps), len(ref_ps))
+    frac = _match_rows(got_ps, ref_ps, tol)
+    gi, ri = _align_rows(got_ps, ref_ps, tol)
+    aligned = len(gi) / max(len(got_ps), len(ref_ps))
+    srms = float(np.sqrt(np.mean(ref_ps[:, 5].astype(np.float64) ** 2)))
+    score_ok = float((np.abs(got_ps[gi, 5] - ref_ps[ri, 5]) <= tol * np.maximum(np.abs(ref_ps[ri, 5]), srms)).mean())
+    head_ok = {}
+    for name in ("cls_pred", "bbox_pred"):
+        a, r = out[name].reshape(len(got_ps), -1)[gi], g[name].reshape(len(ref_ps), -1)[ri]
+        m2 = float(np.mean(r.astype(np.float64) ** 2))
+        # ROIPooling's round() is one more discrete decision: a 0.01-pixel difference in a proposal corner flips it
+        # for a fraction of a percent of the ROIs, and such a row then pools different cells.  The head itself is
+        # checked element by element on identical proposals in the stage-isolated tests.
+        head_ok[name] = float(_rel_ok(a, r, 1e-3, m2).all(axis=1).mean())
+    print(f"[{tag}] proposals {len(got_ps)} vs {len(ref_ps)}: matched {frac:.4f}, aligned in order {aligned:.4f}, "
+          f"scores ok {score_ok:.4f}, head rows within 1e-3 {head_ok}")
+    assert frac >= min_match, f"only {frac:.4f} of the reference proposals matched"
+    assert aligned >= min_aligned, aligned
+    assert score_ok >= min_match
+    for name, v in head_ok.items():
+        assert v >= min_head, (name, v)
+
+
+@pytest.mark.parametrize("precision,feat_tol,row_tol,min_match", [("fp32", 1e-3, 1e-3, 0.997), ("bf16", 6e-2, 5e-2, 0.5)])
 def test_e2e_kitti_7s_vs_reference(cuda, precision, feat_tol, row_tol, min_match):
     from mscnn_b200 import models
     g = np.load(GOLD / "e2e_7s_192x640.npz")
@@ -85,19 +143,7 @@ def test_e2e_kitti_7s_vs_reference(cuda, precision, feat_tol, row_tol, min_match
     frac = _match_rows(got_ps, ref_ps, row_tol)
     assert frac >= min_match, f"only {frac:.4f} of the reference proposals matched"
     if precision == "fp32":
-        # rows in identical order almost everywhere: compare the common prefix directly
-        k = min(len(got_ps), len(ref_ps))
-        ext = np.maximum(np.maximum(ref_ps[:k, 3] - ref_ps[:k, 1], ref_ps[:k, 4] - ref_ps[:k, 2]), 1.0)
-        same = (np.abs(got_ps[:k, 1:5] - ref_ps[:k, 1:5]).max(axis=1) <= row_tol * ext) & (got_ps[:k, 0] == ref_ps[:k, 0])
-        assert same.mean() > 0.5   # rows after a flipped suppression are shifted by one; the prefix before it is aligned
-        # ---- detection head on the rows that are aligned ------------------------------------
-        for name in ("cls_pred", "bbox_pred"):
-            a, r = out[name].reshape(len(got_ps), -1)[:k][same], g[name].reshape(len(ref_ps), -1)[:k][same]
-            m2 = float(np.mean(r.astype(np.float64) ** 2))
-            # ROIPooling's round() is one more discrete decision: a 0.01-pixel difference in a proposal
-            # corner flips it for ~0.5 % of the ROIs, and such a row then pools different cells.  The
-            # head itself is checked element-by-element in test_head_stage_isolated_vs_reference.
-            assert _rel_ok(a, r, 1e-3, m2).mean() >= 0.99, name
+        _check_rows_and_head(out, g, row_tol, min_match, 0.99, 0.98, "7s 192x640")
     print(f"[{precision}] worst trunk rel err {worst}; proposals {len(got_ps)} vs {len(ref_ps)}, matched {frac:.4f}")
 
 
@@ -387,20 +433,7 @@ def test_e2e_kitti_8s_vs_reference(cuda):
         x, ref = net.blob(b), g[b]
         m2 = float(np.mean(ref.astype(np.float64) ** 2))
         assert _rel_ok(x, ref, 1e-3, m2).mean() >= 0.999, b
-    ref_ps = g["proposals_score"].reshape(-1, 6)
-    got_ps = out["proposals_score"].reshape(-1, 6)
-    assert abs(len(got_ps) - len(ref_ps)) <= max(2, 0.01 * len(ref_ps))
-    frac = _match_rows(got_ps, ref_ps, 1e-3)
-    assert frac >= 0.98, f"only {frac:.4f} of the reference proposals matched"
-    k = min(len(got_ps), len(ref_ps))
-    ext = np.maximum(np.maximum(ref_ps[:k, 3] - ref_ps[:k, 1], ref_ps[:k, 4] - ref_ps[:k, 2]), 1.0)
-    same = (np.abs(got_ps[:k, 1:5] - ref_ps[:k, 1:5]).max(axis=1) <= 1e-3 * ext) & (got_ps[:k, 0] == ref_ps[:k, 0])
-    assert same.mean() > 0.5
-    for name in ("cls_pred", "bbox_pred"):
-        a, r = out[name].reshape(len(got_ps), -1)[:k][same], g[name].reshape(len(ref_ps), -1)[:k][same]
-        m2 = float(np.mean(r.astype(np.float64) ** 2))
-        assert _rel_ok(a, r, 1e-3, m2).mean() >= 0.99, name
-    print(f"[8s] proposals {len(got_ps)} vs {len(ref_ps)}, matched {frac:.4f}, aligned prefix {same.mean():.3f}")
+    _check_rows_and_head(out, g, 1e-3, 0.997, 0.99, 0.98, "8s 192x640")
 
 
 def test_e2e_widerface_vs_reference(cuda):
@@ -422,20 +455,7 @@ def test_e2e_widerface_vs_reference(cuda):
         x, ref = net.blob(b), g[b]
         m2 = float(np.mean(ref.astype(np.float64) ** 2))
         assert _rel_ok(x, ref, 1e-3, m2).mean() >= 0.999, b
-    ref_ps = g["proposals_score"].reshape(-1, 6)
-    got_ps = out["proposals_score"].reshape(-1, 6)
-    assert abs(len(got_ps) - len(ref_ps)) <= max(2, 0.01 * len(ref_ps))
-    frac = _match_rows(got_ps, ref_ps, 1e-3)
-    assert frac >= 0.98, f"only {frac:.4f} of the reference proposals matched"
-    k = min(len(got_ps), len(ref_ps))
-    ext = np.maximum(np.maximum(ref_ps[:k, 3] - ref_ps[:k, 1], ref_ps[:k, 4] - ref_ps[:k, 2]), 1.0)
-    same = (np.abs(got_ps[:k, 1:5] - ref_ps[:k, 1:5]).max(axis=1) <= 1e-3 * ext) & (got_ps[:k, 0] == ref_ps[:k, 0])
-    assert same.mean() > 0.5
-    for name in ("cls_pred", "bbox_pred"):
-        a, r = out[name].reshape(len(got_ps), -1)[:k][same], g[name].reshape(len(ref_ps), -1)[:k][same]
-        m2 = float(np.mean(r.astype(np.float64) ** 2))
-        assert _rel_ok(a, r, 1e-3, m2).mean() >= 0.99, name
-    print(f"[wider] proposals {len(got_ps)} vs {len(ref_ps)}, matched {frac:.4f}, aligned prefix {same.mean():.3f}")
+    _check_rows_and_head(out, g, 1e-3, 0.997, 0.99, 0.98, "wider 128x192")
 
 
 def test_async_input_upload_pipelines_correctly(cuda):
