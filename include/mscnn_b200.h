@@ -291,6 +291,14 @@ MSCNN_API int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const
                              void* workspace, size_t workspace_bytes, float* dets, int* det_counts,
                              void* stream);
 
+/* Packed output of the same post-process, for the multi-GPU exchange below: `payload` (device,
+ * mscnn_detect_payload_floats(N, max_rois_per_image) floats) = int32 header [N, total, counts[0..N)] padded to a
+ * multiple of 4 words, then the kept rows of all N images back to back, [total][5] = [x y w h prob] in image order. */
+MSCNN_API size_t mscnn_detect_payload_floats(int N, int max_rois_per_image);
+MSCNN_API int mscnn_detect_postprocess_packed(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
+                                    const float* cls_pred, const float* bbox_pred, const int* num_rois,
+                                    void* workspace, size_t workspace_bytes, float* payload, void* stream);
+
 /* Cascade variant: replaces the MATLAB code after net.forward in examples/kitti_car/run_cascademscnn.m:99-126
  * (+ utils/bbNms.m:112-126).  The net already holds decoded boxes and probabilities:
  *   proposals [R][5] (the stage's ROIs: rows whose width or height is 0 are dropped), cls_prob [R][num_cls]
@@ -414,6 +422,35 @@ MSCNN_API int mscnn_net_detect(void* net, const mscnn_detect_cfg* cfg, float* de
 MSCNN_API int mscnn_net_detect_cascade(void* net, const mscnn_detect_cfg* cfg, const char* proposals_blob,
                              const char* cls_prob_blob, const char* output_bbox_blob, float* dets_dev,
                              int* det_counts_dev);
+
+
+/* ------------------------------------------------------------------------------------
+ * Multi-GPU exchange.  The reference has no multi-GPU inference (P2PSync is training-only,
+ * src/caffe/parallel.cpp:421-439); images are independent, so batches are sharded by image with no data-path
+ * collective, and the ONE exchange is an all-gather of the final detections.  What is mirrored is the reference's
+ * threading model: one Caffe context per host thread (src/caffe/common.cpp:13-22) = one communicator rank per host
+ * thread (mscnn_comm_init_all, one process) or per process (mscnn_comm_init_rank; the 128-byte id from rank 0's
+ * mscnn_comm_get_unique_id travels by whatever the host has: MPI, torch.distributed, a file).
+ * NCCL is bound at run time (libnccl.so.2 already in the process, else $MSCNN_NCCL_LIB, else the loader path).
+ *
+ * mscnn_comm_all_gather: in-place ncclAllGather of `floats_per_rank` floats per rank (rank r's part at
+ *   buf_all + r * floats_per_rank, produced on `producer_stream`); it runs on the communicator's own stream behind
+ *   the producer's current tail, so the producer continues with the next step while the gather is in flight.
+ * mscnn_comm_stream_wait / mscnn_comm_synchronize: order a stream / the host behind the last gather.
+ * mscnn_net_detect_gather: mscnn_net_detect in packed form straight into this rank's slot of payload_all
+ *   ([nranks][mscnn_detect_payload_floats(N, cap)] floats, device) + the all-gather: one collective per step, the
+ *   per-image counts ride in the payload header.  All ranks must use the same N and max_rois_per_image. */
+#define MSCNN_COMM_ID_BYTES 128
+MSCNN_API int mscnn_comm_nccl_version(void); /* 0 if NCCL cannot be loaded */
+MSCNN_API int mscnn_comm_get_unique_id(void* host_id128);
+MSCNN_API int mscnn_comm_init_rank(void** comm, int nranks, int rank, const void* host_id128); /* current device */
+MSCNN_API int mscnn_comm_init_all(void** comms, int ndev, const int* devices /* NULL = 0..ndev-1 */);
+MSCNN_API int mscnn_comm_destroy(void* comm);
+MSCNN_API int mscnn_comm_info(void* comm, int* nranks, int* rank, int* device);
+MSCNN_API int mscnn_comm_all_gather(void* comm, float* buf_all, size_t floats_per_rank, void* producer_stream);
+MSCNN_API int mscnn_comm_stream_wait(void* comm, void* stream);
+MSCNN_API int mscnn_comm_synchronize(void* comm);
+MSCNN_API int mscnn_net_detect_gather(void* net, const mscnn_detect_cfg* cfg, void* comm, float* payload_all);
 
 #ifdef __cplusplus
 }

@@ -501,6 +501,35 @@ __global__ void detect_write_kernel(const float4* __restrict__ sboxes, const flo
   if (threadIdx.x == 0) det_counts[n] = cnt;
 }
 
+// Packed form for the multi-GPU exchange ("fuse the device-side compaction that produces the send
+// buffer with the post-process kernel"): payload = int32 header [N, total, counts[0..N)] padded to a multiple of 4
+// words, then the kept rows of all images back to back, [total][5] = [x y w h prob] in image order.  One block per
+// image; its row offset is the sum of the (capped) counts of the images before it.
+__global__ void detect_write_packed_kernel(const float4* __restrict__ sboxes, const float* __restrict__ sscores,
+                                           const int* __restrict__ keep_idx, const int* __restrict__ keep_count,
+                                           int Kpad, int cap, int N, float* __restrict__ payload) {
+  const int n = blockIdx.x;
+  int off = 0;
+  for (int m = 0; m < n; ++m) off += min(keep_count[m], cap);
+  const int cnt = min(keep_count[n], cap);
+  const int hdr = (2 + N + 3) & ~3;
+  int* head = reinterpret_cast<int*>(payload);
+  float* rows = payload + hdr + (size_t)off * 5;
+  for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+    const int src = keep_idx[(size_t)n * Kpad + r];
+    const float4 b = sboxes[(size_t)n * Kpad + src];
+    float* o = rows + (size_t)r * 5;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = sscores[(size_t)n * Kpad + src];
+  }
+  if (threadIdx.x == 0) {
+    head[2 + n] = cnt;
+    if (n == N - 1) {
+      head[0] = N;
+      head[1] = off + cnt;
+    }
+  }
+}
+
 static int next_pow2(int v) {
   int p = 64;
   while (p < v) p <<= 1;
@@ -677,12 +706,12 @@ extern "C" int mscnn_detect_workspace_bytes(const mscnn_detect_cfg* cfg, int N, 
 
 static int detect_run(bool cascade, const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
                       const float* cls_pred, const float* bbox_pred, const int* num_rois, void* workspace,
-                      size_t workspace_bytes, float* dets, int* det_counts, void* stream_v) {
+                      size_t workspace_bytes, float* dets, int* det_counts, void* stream_v, float* payload = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_v;
   int Kpad;
   const int rc = det_cfg_check(cfg, N, &Kpad);
   if (rc) return rc;
-  if (!proposals_score || !cls_pred || !bbox_pred || !num_rois || !workspace || !dets || !det_counts)
+  if (!proposals_score || !cls_pred || !bbox_pred || !num_rois || !workspace || (!payload && (!dets || !det_counts)))
     return MSCNN_ERR_INVALID;
   const DetWs w = plan_det_ws(N, Kpad);
   if (workspace_bytes < w.total) return MSCNN_ERR_NOMEM;
@@ -725,8 +754,12 @@ static int detect_run(bool cascade, const mscnn_detect_cfg* cfg, int N, const fl
   mscnn::note_launch();
   nms_scan_kernel<<<N, kScanThreads, scan_smem, stream>>>(mask, counts, Kpad, words, 0, keep_idx, keep_count);
   mscnn::note_launch();
-  detect_write_kernel<<<N, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, Kpad,
-                                            cfg->max_rois_per_image, dets, det_counts);
+  if (payload)
+    detect_write_packed_kernel<<<N, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, Kpad,
+                                                     cfg->max_rois_per_image, N, payload);
+  else
+    detect_write_kernel<<<N, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, Kpad,
+                                              cfg->max_rois_per_image, dets, det_counts);
   e = cudaGetLastError();
   if (e != cudaSuccess) {
     fprintf(stderr, "mscnn_detect_postprocess: %s\n", cudaGetErrorString(e));
@@ -741,6 +774,19 @@ extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, cons
                                         int* det_counts, void* stream) {
   return detect_run(false, cfg, N, proposals_score, cls_pred, bbox_pred, num_rois, workspace, workspace_bytes,
                     dets, det_counts, stream);
+}
+
+extern "C" size_t mscnn_detect_payload_floats(int N, int max_rois_per_image) {
+  if (N <= 0 || max_rois_per_image <= 0) return 0;
+  return (size_t)((2 + N + 3) & ~3) + (size_t)N * max_rois_per_image * 5;
+}
+
+extern "C" int mscnn_detect_postprocess_packed(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
+                                               const float* cls_pred, const float* bbox_pred, const int* num_rois,
+                                               void* workspace, size_t workspace_bytes, float* payload, void* stream) {
+  if (!payload) return MSCNN_ERR_INVALID;
+  return detect_run(false, cfg, N, proposals_score, cls_pred, bbox_pred, num_rois, workspace, workspace_bytes,
+                    nullptr, nullptr, stream, payload);
 }
 
 extern "C" int mscnn_cascade_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals,

@@ -220,6 +220,10 @@ class CAFFE_API BoxOutputLayer : public Layer<Dtype> {
   const int* num_out_device() const { return num_out_dev_; }   // int[2+N], see mscnn_box_output_forward
   int num_proposals() const { return num_out_host_ ? num_out_host_[1] : 0; }
   int image_proposals(int n) const { return num_out_host_[2 + n]; }
+  // upper bound of the proposals one image can contribute (box_output_layer.cpp:176-186)
+  int max_rows_per_image() const {
+    return (cfg_.max_post_nms_num > 0 && cfg_.max_post_nms_num < cfg_.max_nms_num) ? cfg_.max_post_nms_num : cfg_.max_nms_num;
+  }
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
   mscnn_box_output_cfg cfg_;

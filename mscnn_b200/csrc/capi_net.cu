@@ -323,6 +323,13 @@ int mscnn_net_detect(void* hv, const mscnn_detect_cfg* cfg, float* dets_dev, int
       !h->net->has_blob("bbox_pred"))
     return MSCNN_ERR_INVALID;
   const int N = h->net->input_blobs()[0]->num();
+  // The post-process keeps every proposal of an image (run_mscnn_detection.m:75-120 has no cap): a cfg whose
+  // max_rois_per_image is below what BoxOutput can emit would silently drop rows, so it is refused instead.
+  if (cfg->max_rois_per_image < h->box->max_rows_per_image()) {
+    fprintf(stderr, "mscnn_net_detect: max_rois_per_image = %d < %d proposals an image can carry (BoxOutput max_nms_num / "
+            "max_post_nms_num)\n", cfg->max_rois_per_image, h->box->max_rows_per_image());
+    return MSCNN_ERR_INVALID;
+  }
   size_t need = 0;
   int rc = mscnn_detect_workspace_bytes(cfg, N, &need);
   if (rc) return rc;
@@ -336,6 +343,42 @@ int mscnn_net_detect(void* hv, const mscnn_detect_cfg* cfg, float* dets_dev, int
                                   h->net->blob_by_name("bbox_pred")->gpu_data(), h->box->num_out_device(),
                                   h->det_ws, h->det_ws_bytes, dets_dev, det_counts_dev, Caffe::stream());
 }
+// Final detections of this rank's images, packed (header + compacted rows), then ONE all-gather on the communicator's
+// stream.  The producer stream first waits for the previous gather (it still reads / writes payload_all).
+int mscnn_net_detect_gather(void* hv, const mscnn_detect_cfg* cfg, void* comm, float* payload_all) {
+  NetHandle* h = H(hv);
+  if (!h->box || !comm || !payload_all || !h->net->has_blob("proposals_score") || !h->net->has_blob("cls_pred") ||
+      !h->net->has_blob("bbox_pred"))
+    return MSCNN_ERR_INVALID;
+  const int N = h->net->input_blobs()[0]->num();
+  // The post-process keeps every proposal of an image (run_mscnn_detection.m:75-120 has no cap): a cfg whose
+  // max_rois_per_image is below what BoxOutput can emit would silently drop rows, so it is refused instead.
+  if (cfg->max_rois_per_image < h->box->max_rows_per_image()) {
+    fprintf(stderr, "mscnn_net_detect: max_rois_per_image = %d < %d proposals an image can carry (BoxOutput max_nms_num / "
+            "max_post_nms_num)\n", cfg->max_rois_per_image, h->box->max_rows_per_image());
+    return MSCNN_ERR_INVALID;
+  }
+  int nranks = 0, rank = 0;
+  int rc = mscnn_comm_info(comm, &nranks, &rank, nullptr);
+  if (rc) return rc;
+  size_t need = 0;
+  rc = mscnn_detect_workspace_bytes(cfg, N, &need);
+  if (rc) return rc;
+  if (need > h->det_ws_bytes) {
+    if (h->det_ws) cudaFree(h->det_ws);
+    if (cudaMalloc(&h->det_ws, need) != cudaSuccess) return MSCNN_ERR_NOMEM;
+    h->det_ws_bytes = need;
+  }
+  const size_t per = mscnn_detect_payload_floats(N, cfg->max_rois_per_image);
+  rc = mscnn_comm_stream_wait(comm, Caffe::stream());
+  if (rc) return rc;
+  rc = mscnn_detect_postprocess_packed(cfg, N, h->net->blob_by_name("proposals_score")->gpu_data(),
+                                       h->net->blob_by_name("cls_pred")->gpu_data(),
+                                       h->net->blob_by_name("bbox_pred")->gpu_data(), h->box->num_out_device(),
+                                       h->det_ws, h->det_ws_bytes, payload_all + (size_t)rank * per, Caffe::stream());
+  if (rc) return rc;
+  return mscnn_comm_all_gather(comm, payload_all, per, Caffe::stream());
+}
 int mscnn_net_detect_cascade(void* hv, const mscnn_detect_cfg* cfg, const char* proposals_blob,
                              const char* cls_prob_blob, const char* output_bbox_blob, float* dets_dev,
                              int* det_counts_dev) {
@@ -344,6 +387,13 @@ int mscnn_net_detect_cascade(void* hv, const mscnn_detect_cfg* cfg, const char* 
       !h->net->has_blob(cls_prob_blob) || !h->net->has_blob(output_bbox_blob))
     return MSCNN_ERR_INVALID;
   const int N = h->net->input_blobs()[0]->num();
+  // The post-process keeps every proposal of an image (run_mscnn_detection.m:75-120 has no cap): a cfg whose
+  // max_rois_per_image is below what BoxOutput can emit would silently drop rows, so it is refused instead.
+  if (cfg->max_rois_per_image < h->box->max_rows_per_image()) {
+    fprintf(stderr, "mscnn_net_detect: max_rois_per_image = %d < %d proposals an image can carry (BoxOutput max_nms_num / "
+            "max_post_nms_num)\n", cfg->max_rois_per_image, h->box->max_rows_per_image());
+    return MSCNN_ERR_INVALID;
+  }
   size_t need = 0;
   int rc = mscnn_detect_workspace_bytes(cfg, N, &need);
   if (rc) return rc;

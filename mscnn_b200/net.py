@@ -53,6 +53,8 @@ def _declare(L):
     L.mscnn_net_layer_times.argtypes = [C.c_void_p, C.c_void_p]
     L.mscnn_net_num_proposals.argtypes = [C.c_void_p, C.c_int]
     L.mscnn_net_detect.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_void_p, C.c_void_p]
+    L.mscnn_net_detect_gather.restype = C.c_int
+    L.mscnn_net_detect_gather.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_void_p, C.c_void_p]
     L.mscnn_net_detect_cascade.restype = C.c_int
     L.mscnn_net_detect_cascade.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_char_p, C.c_char_p, C.c_char_p,
                                            C.c_void_p, C.c_void_p]
@@ -231,6 +233,11 @@ class Net:
 
     def detect(self, cfg: capi.DetectCfg, dets_dev_ptr: int, counts_dev_ptr: int) -> None:
         capi.check(self._L.mscnn_net_detect(self._h, cfg, dets_dev_ptr, counts_dev_ptr), "net_detect")
+
+    def detect_gather(self, cfg: capi.DetectCfg, comm, payload_all_ptr: int) -> None:
+        """Final detections of this rank packed into its slot of `payload_all` + ONE all-gather on the communicator's
+        stream (mscnn_net_detect_gather); `comm` is a parallel.Comm."""
+        capi.check(self._L.mscnn_net_detect_gather(self._h, cfg, comm.handle, payload_all_ptr), "net_detect_gather")
 
     def detect_cascade(self, cfg: capi.DetectCfg, dets_dev_ptr: int, counts_dev_ptr: int, stage: str = "3rd",
                        cls_prob: str | None = None) -> None:

@@ -44,6 +44,8 @@ def lib() -> C.CDLL:
         L.mscnn_ref_net_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
         L.mscnn_ref_blas_backend.restype = C.c_char_p
         L.mscnn_ref_blas_threads.restype = C.c_int
+        L.mscnn_ref_blas_set_threads.restype = C.c_int
+        L.mscnn_ref_blas_set_threads.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -54,6 +56,11 @@ def blas_backend() -> str:
 
 def blas_threads() -> int:
     return int(lib().mscnn_ref_blas_threads())
+
+
+def set_blas_threads(n: int) -> int:
+    """Pin the BLAS thread count explicitly (torchrun exports OMP_NUM_THREADS=1); returns the count in effect."""
+    return int(lib().mscnn_ref_blas_set_threads(int(n)))
 
 
 class RefNet:

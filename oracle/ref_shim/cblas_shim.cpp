@@ -30,6 +30,8 @@ struct Backend {
   dgemv_fn dgemv = nullptr;
   std::string name = "builtin";
   int threads = 1;
+  void (*set_threads)(int) = nullptr;
+  int (*get_threads)(void) = nullptr;
 };
 
 Backend load_backend() {
@@ -72,8 +74,11 @@ Backend load_backend() {
         b.sgemm = s; b.dgemm = d; b.sgemv = sv; b.dgemv = dv;
         b.name = "openblas:" + c;
         typedef int (*nthr_fn)(void);
-        if (nthr_fn nt = reinterpret_cast<nthr_fn>(dlsym(h, (pf + "openblas_get_num_threads").c_str())))
+        if (nthr_fn nt = reinterpret_cast<nthr_fn>(dlsym(h, (pf + "openblas_get_num_threads").c_str()))) {
           b.threads = nt();
+          b.get_threads = nt;
+        }
+        b.set_threads = reinterpret_cast<void (*)(int)>(dlsym(h, (pf + "openblas_set_num_threads").c_str()));
         return b;
       }
     }
@@ -146,6 +151,20 @@ extern "C" {
 
 const char* mscnn_ref_blas_backend(void) { return backend().name.c_str(); }
 int mscnn_ref_blas_threads(void) { return backend().threads; }
+// Explicit thread count for the BLAS behind the reference layers (torchrun exports OMP_NUM_THREADS=1, which would
+// silently turn the "all host cores" baseline into a single-threaded one).  Returns the count in effect.
+int mscnn_ref_blas_set_threads(int n) {
+  Backend& b = backend();
+  if (n < 1) n = 1;
+  if (b.set_threads) {
+    b.set_threads(n);
+    b.threads = b.get_threads ? b.get_threads() : n;
+  } else {
+    omp_set_num_threads(n);
+    b.threads = omp_get_max_threads();
+  }
+  return b.threads;
+}
 
 void cblas_sgemm(const enum CBLAS_ORDER o, const enum CBLAS_TRANSPOSE ta, const enum CBLAS_TRANSPOSE tb,
                  const int M, const int N, const int K, const float alpha, const float* A,
