@@ -239,70 +239,95 @@ __global__ void nms_mask_kernel(const float4* __restrict__ boxes, const int* __r
   mask[((size_t)n * Kpad + i) * words + cb] = bits;
 }
 
-// Greedy scan (nmsMax with greedy=true, box_output_layer.cpp:46-56).  One CTA per image walks the
-// boxes in blocks of 64: the block's mask rows are staged in shared memory with coalesced loads,
-// one thread resolves the 64 intra-block decisions on the diagonal word, then every thread ORs
-// the kept rows into the suppression words of the later blocks.
+// Greedy scan (nmsMax with greedy=true, box_output_layer.cpp:46-56).  One CTA per image walks the boxes in blocks of
+// 64.  The greedy order is a true dependence chain (box i survives iff no EARLIER SURVIVOR suppresses it), so the
+// work per block is arranged around the chain:
+//   * diagonal: warp 0 holds the block's 64 diagonal mask words in registers (lane l: rows l and l + 32) and resolves
+//     the 64 intra-block decisions with shuffles -- no memory access on the chain;
+//   * meanwhile warps 1..7 stage the NEXT block's mask rows in the other shared-memory buffer (coalesced);
+//   * suppression of the later words: all 256 threads, thread (part, word) ORs the kept rows 8 part .. 8 part + 7 of
+//     one word and merges with a shared-memory atomicOr (was: one warp, 64 dependent loads per thread);
+//   * compaction of the survivors' indices by block-parallel prefix sums of the kept-bit popcounts.
+// Previous version (one thread on the diagonal reading shared memory, no prefetch): 0.29 ms per launch at M = 2000
+// (profiles/r01i_summary.md); this one: profiles/r02_summary.md.
 constexpr int kScanThreads = 256;
 __global__ void __launch_bounds__(kScanThreads)
 nms_scan_kernel(const unsigned long long* __restrict__ mask, const int* __restrict__ counts, int Kpad,
                 int words, int max_post, int* __restrict__ keep_idx, int* __restrict__ keep_count) {
-  extern __shared__ unsigned long long tile[];  // [64][words]
+  extern __shared__ unsigned long long tile[];  // 2 x [64][words]
   __shared__ unsigned long long remv[128];
   __shared__ unsigned long long kept[128];
+  __shared__ int kept_off[129];
   __shared__ unsigned long long s_keptbits;
-  const int n = blockIdx.x, tid = threadIdx.x;
+  const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int M = counts[n];
   const int nb = (M + 63) / 64;
   const unsigned long long* mk = mask + (size_t)n * Kpad * words;
+  const int tile_words = 64 * words;
   for (int w = tid; w < 128; w += kScanThreads) { remv[w] = 0ull; kept[w] = 0ull; }
-  __syncthreads();
-  for (int b = 0; b < nb; ++b) {
+  // stage block b's rows (words b .. nb - 1 only: earlier words are never read) with threads [t0, t0 + nt)
+  auto stage = [&](int b, unsigned long long* dst, int t0, int nt) {
     const int rows = min(64, M - b * 64);
     const int wcount = nb - b;
-    for (int idx = tid; idx < rows * wcount; idx += kScanThreads) {
+    for (int idx = tid - t0; idx < rows * wcount; idx += nt) {
       const int r = idx / wcount, w = b + idx - r * wcount;
-      tile[r * words + w] = mk[(size_t)(b * 64 + r) * words + w];
+      dst[r * words + w] = mk[(size_t)(b * 64 + r) * words + w];
     }
-    __syncthreads();
-    if (tid == 0) {
+  };
+  if (nb > 0) stage(0, tile, 0, kScanThreads);
+  __syncthreads();
+  for (int b = 0; b < nb; ++b) {
+    const unsigned long long* cur_tile = tile + (b & 1) * tile_words;
+    const int rows = min(64, M - b * 64);
+    if (warp == 0) {
+      const unsigned long long d0 = lane < rows ? cur_tile[lane * words + b] : 0ull;
+      const unsigned long long d1 = lane + 32 < rows ? cur_tile[(lane + 32) * words + b] : 0ull;
       unsigned long long cur = remv[b], kb = 0ull;
-      for (int i = 0; i < rows; ++i) {
-        if (!((cur >> i) & 1ull)) {
+#pragma unroll 8
+      for (int i = 0; i < 64; ++i) {
+        const unsigned long long wi = __shfl_sync(0xffffffffu, i < 32 ? d0 : d1, i & 31);
+        if (i < rows && !((cur >> i) & 1ull)) {
           kb |= (1ull << i);
-          cur |= tile[i * words + b];
+          cur |= wi;
         }
       }
-      s_keptbits = kb;
-      kept[b] = kb;
+      if (lane == 0) {
+        s_keptbits = kb;
+        kept[b] = kb;
+      }
+    } else if (b + 1 < nb) {
+      stage(b + 1, tile + ((b + 1) & 1) * tile_words, 32, kScanThreads - 32);
     }
     __syncthreads();
     const unsigned long long kb = s_keptbits;
-    for (int w = b + 1 + tid; w < nb; w += kScanThreads) {
-      unsigned long long acc = remv[w];
-      unsigned long long bits = kb;
-      while (bits) {
-        const int i = __ffsll((long long)bits) - 1;
-        bits &= bits - 1;
-        acc |= tile[i * words + w];
+    const int part = tid >> 5;  // rows 8 part .. 8 part + 7
+    const unsigned long long kpart = (kb >> (8 * part)) & 0xFFull;
+    if (kpart) {
+      for (int w = b + 1 + lane; w < nb; w += 32) {
+        unsigned long long acc = 0ull;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if ((kpart >> i) & 1ull) acc |= cur_tile[(8 * part + i) * words + w];
+        if (acc) atomicOr(&remv[w], acc);
       }
-      remv[w] = acc;
     }
     __syncthreads();
   }
+  // survivors' indices in order: exclusive prefix of the per-block popcounts (nb <= 128)
   if (tid == 0) {
-    int r = 0;
-    for (int b = 0; b < nb; ++b) {
-      unsigned long long bits = kept[b];
-      while (bits) {
-        const int i = __ffsll((long long)bits) - 1;
-        bits &= bits - 1;
-        if (max_post <= 0 || r < max_post) keep_idx[(size_t)n * Kpad + r] = b * 64 + i;
-        ++r;
-      }
+    int acc = 0;
+    for (int b = 0; b < nb; ++b) { kept_off[b] = acc; acc += __popcll(kept[b]); }
+    kept_off[nb] = acc;
+    keep_count[n] = (max_post > 0 && acc > max_post) ? max_post : acc;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < nb * 64; idx += kScanThreads) {
+    const int b = idx >> 6, i = idx & 63;
+    const unsigned long long bits = kept[b];
+    if ((bits >> i) & 1ull) {
+      const int r = kept_off[b] + __popcll(bits & ((1ull << i) - 1ull));
+      if (max_post <= 0 || r < max_post) keep_idx[(size_t)n * Kpad + r] = b * 64 + i;
     }
-    if (max_post > 0 && r > max_post) r = max_post;
-    keep_count[n] = r;
   }
 }
 
@@ -649,7 +674,7 @@ extern "C" int mscnn_box_output_forward(const mscnn_box_output_cfg* cfg, int N, 
   mscnn::note_launch();
   nms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words, cfg->iou_thr,
                                                            cfg->nms_type, mask);
-  const size_t scan_smem = (size_t)64 * words * 8;
+  const size_t scan_smem = (size_t)2 * 64 * words * 8;
   e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
   if (e != cudaSuccess) return MSCNN_ERR_CUDA;
   mscnn::note_launch();
@@ -748,7 +773,7 @@ static int detect_run(bool cascade, const mscnn_detect_cfg* cfg, int N, const fl
   mscnn::note_launch();
   bbnms_mask_kernel<<<dim3(words, words, N), 64, 0, stream>>>(sboxes, counts, Kpad, words,
                                                              (double)cfg->nms_overlap, mask);
-  const size_t scan_smem = (size_t)64 * words * 8;
+  const size_t scan_smem = (size_t)2 * 64 * words * 8;
   e = cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
   if (e != cudaSuccess) return MSCNN_ERR_CUDA;
   mscnn::note_launch();

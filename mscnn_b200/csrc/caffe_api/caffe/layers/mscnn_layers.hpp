@@ -241,7 +241,7 @@ template <typename Dtype>
 class CAFFE_API ROIPoolingLayer : public Layer<Dtype> {
  public:
   explicit ROIPoolingLayer(const LayerParameter& param)
-      : Layer<Dtype>(param), concat_top_(nullptr), concat_offset_(0), concat_channels_(0) {}
+      : Layer<Dtype>(param), concat_top_(nullptr), concat_offset_(0), concat_channels_(0), rows_source_(nullptr) {}
   virtual void LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
   virtual void Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
   virtual inline const char* type() const { return "ROIPooling"; }
@@ -249,6 +249,9 @@ class CAFFE_API ROIPoolingLayer : public Layer<Dtype> {
   virtual inline int MaxBottomBlobs() const { return 2; }
   virtual inline int MinTopBlobs() const { return 1; }
   virtual inline int MaxTopBlobs() const { return 1; }
+  // mscnn_b200 extension (set by Net): the BoxOutput layer this layer's ROI list descends from (per-image row counts
+  // for the gather schedule; NULL = unknown origin, plain schedule).
+  void set_rows_source(const BoxOutputLayer<Dtype>* box) { rows_source_ = box; }
   // mscnn_b200 extension (set by Net): write into `target` (the Concat top) at a channel offset.
   void set_concat_target(Blob<Dtype>* target, int channel_offset, int total_channels) {
     concat_top_ = target; concat_offset_ = channel_offset; concat_channels_ = total_channels;
@@ -274,6 +277,7 @@ class CAFFE_API ROIPoolingLayer : public Layer<Dtype> {
   float spatial_scale_, pad_ratio_;
   Blob<Dtype>* concat_top_;
   int concat_offset_, concat_channels_;
+  const BoxOutputLayer<Dtype>* rows_source_;
   vector<Sibling> siblings_;
   bool done_by_leader_ = false;
 };

@@ -129,6 +129,59 @@ struct RoiVariants {
   int c_off[4];
 };
 
+// Pools one (ROI, bin, variant) window for the channel groups g0 + lane (+ 32 when DUAL) and stores the result.
+// The window is walked as one flattened pixel sequence in 16-byte units with 32-bit indices (the feature map has
+// < 2^31 / 8 elements: checked by the launcher), two pixels per step, so up to eight 16-byte loads (hi, lo, second
+// group) are in flight per lane: the kernel was bound by the latency of two (profiles/r01h_summary.md).  fmaxf gives the
+// reference's `if (x > max) max = x` result for every non-NaN input.  Stores are streaming (st.global.cs).
+template <bool DUAL>
+__device__ __forceinline__ void roi_pool_window(const uint4* __restrict__ xh4, const uint4* __restrict__ xl4, int base_idx,
+                                                int npx, int bw, int row_skip, int cg, bool empty,
+                                                __nv_bfloat16* yh, __nv_bfloat16* yl, size_t out_off) {
+  const bool has_lo = xl4 != nullptr;
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  Vec8 best0, best1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) best0.v[i] = best1.v[i] = empty ? 0.f : -3.402823466e+38f;
+  int idx = base_idx;
+  int wpos = 0;
+  int k = 0;
+  for (; k + 2 <= npx; k += 2) {
+    int ix[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      ix[u] = idx;
+      idx += cg;
+      if (++wpos == bw) { wpos = 0; idx += row_skip; }
+    }
+    uint4 a[2], l[2], c[2], m[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      a[u] = __ldg(xh4 + ix[u]);
+      l[u] = has_lo ? __ldg(xl4 + ix[u]) : z;
+      if (DUAL) {
+        c[u] = __ldg(xh4 + ix[u] + 32);
+        m[u] = has_lo ? __ldg(xl4 + ix[u] + 32) : z;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      max8(best0, a[u], l[u], has_lo);
+      if (DUAL) max8(best1, c[u], m[u], has_lo);
+    }
+  }
+  if (k < npx) {
+    max8(best0, __ldg(xh4 + idx), has_lo ? __ldg(xl4 + idx) : z, has_lo);
+    if (DUAL) max8(best1, __ldg(xh4 + idx + 32), has_lo ? __ldg(xl4 + idx + 32) : z, has_lo);
+  }
+  store8<true>(yh, yl, out_off, best0);
+  if (DUAL) store8<true>(yh, yl, out_off + 32 * 8, best1);
+}
+
+// One warp per (ROI, bin); a lane owns channel groups g and g + 32 (C = 512: all 64 groups in one visit).
+// Schedules that were measured and dropped (profiles/r02_summary.md): per-image half-channel passes (halves the L2
+// working set: DRAM reads 3.27 -> 2.83 GB but 1.74 -> 2.15 ms), block-per-ROI (L1 sharing between the bins of one ROI:
+// 1.79 -> 2.02 ms), createpolicy evict_last loads / evict_first stores (no change).
 __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
                                 const float* __restrict__ rois, int R, int N, int H, int W, int C,
                                 int PH, int PW, float scale, const RoiVariants var,
@@ -137,6 +190,8 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
   const int lane = threadIdx.x & 31;
   const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
   const size_t bins = (size_t)R * PH * PW;
+  const uint4* xh4 = reinterpret_cast<const uint4*>(xh);
+  const uint4* xl4 = reinterpret_cast<const uint4*>(xl);
   for (size_t bin = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); bin < bins; bin += warps_total) {
     const int pw = bin % PW;
     const int ph = (bin / PW) % PH;
@@ -163,63 +218,14 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
       wstart = min(max(wstart + sw, 0), W);
       wend = min(max(wend + sw, 0), W);
       const bool empty = (hend <= hstart) || (wend <= wstart);
-      // 16-byte units, 32-bit indices (the feature map has < 2^31 / 8 elements: checked by the launcher).  The
-      // window is walked as one flattened pixel sequence, two pixels per step, and a lane owns channel groups g and
-      // g + 32 at once (C = 512: cg = 64), so up to eight 16-byte loads are in flight per lane: the kernel was
-      // bound by the latency of two (profiles/r01h_summary.md).  fmaxf gives the reference's
-      // `if (x > max) max = x` result for every non-NaN input.
-      const uint4* xh4 = reinterpret_cast<const uint4*>(xh);
-      const uint4* xl4 = reinterpret_cast<const uint4*>(xl);
-      const bool has_lo = xl != nullptr;
       const int bw = wend - wstart;
       const int npx = empty ? 0 : (hend - hstart) * bw;
       const int row_skip = (W - bw) * cg;
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      const int base = ((b * H + hstart) * W + wstart) * cg;
+      const size_t out = (size_t)bin * Ctot + var.c_off[vi];
       for (int g = lane; g < cg; g += 64) {
-        const bool dual = g + 32 < cg;
-        Vec8 best0, best1;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) best0.v[i] = best1.v[i] = empty ? 0.f : -3.402823466e+38f;
-        int idx = ((b * H + hstart) * W + wstart) * cg + g;
-        int wpos = 0;
-        int k = 0;
-        for (; k + 1 < npx; k += 2) {
-          const int i0 = idx;
-          idx += cg;
-          if (++wpos == bw) { wpos = 0; idx += row_skip; }
-          const int i1 = idx;
-          idx += cg;
-          if (++wpos == bw) { wpos = 0; idx += row_skip; }
-          const uint4 a0 = __ldg(xh4 + i0), a1 = __ldg(xh4 + i1);
-          const uint4 c0 = dual ? __ldg(xh4 + i0 + 32) : z, c1 = dual ? __ldg(xh4 + i1 + 32) : z;
-          uint4 l0 = z, l1 = z, m0 = z, m1 = z;
-          if (has_lo) {
-            l0 = __ldg(xl4 + i0);
-            l1 = __ldg(xl4 + i1);
-            if (dual) {
-              m0 = __ldg(xl4 + i0 + 32);
-              m1 = __ldg(xl4 + i1 + 32);
-            }
-          }
-          max8(best0, a0, l0, has_lo);
-          max8(best0, a1, l1, has_lo);
-          if (dual) {
-            max8(best1, c0, m0, has_lo);
-            max8(best1, c1, m1, has_lo);
-          }
-        }
-        if (k < npx) {
-          const uint4 a0 = __ldg(xh4 + idx);
-          const uint4 l0 = has_lo ? __ldg(xl4 + idx) : z;
-          max8(best0, a0, l0, has_lo);
-          if (dual) {
-            const uint4 c0 = __ldg(xh4 + idx + 32);
-            const uint4 m0 = has_lo ? __ldg(xl4 + idx + 32) : z;
-            max8(best1, c0, m0, has_lo);
-          }
-        }
-        store8<true>(yh, yl, (size_t)bin * Ctot + var.c_off[vi] + g * 8, best0);
-        if (dual) store8<true>(yh, yl, (size_t)bin * Ctot + var.c_off[vi] + (g + 32) * 8, best1);
+        if (g + 32 < cg) roi_pool_window<true>(xh4, xl4, base + g, npx, bw, row_skip, cg, empty, yh, yl, out + g * 8);
+        else roi_pool_window<false>(xh4, xl4, base + g, npx, bw, row_skip, cg, empty, yh, yl, out + g * 8);
       }
     }
   }
