@@ -99,6 +99,11 @@ typedef struct mscnn_conv_desc {
    * NULL: the un-pooled tensor is then never written to HBM. */
   void* pool_hi;
   void* pool_lo;
+  /* Optional data-dependent batch size (device int, may be NULL): the kernel processes min(*dyn_n, N) images / rows
+   * and leaves the rest of y untouched.  The detection head runs on BoxOutput's R proposals, a count that only exists
+   * on the device when the head is launched (the reference learns it on the host, box_output_layer.cpp:201): the
+   * launch is sized for the cap N and R is read by the kernel. */
+  const int* dyn_n;
 } mscnn_conv_desc;
 MSCNN_API int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream);
 
@@ -173,6 +178,21 @@ MSCNN_API int mscnn_pack_conv1_pair_weights(const float* w_f32 /*[Cout][3][3][3]
  *   Ho = ceil((H - kernel) / stride) + 1.  mode = MSCNN_POOL_MAX | MSCNN_POOL_AVE. */
 MSCNN_API int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H, int W,
                        int C, int kernel, int stride, int mode, void* stream);
+
+/* Data-dependent row counts.  The three per-ROI kernels behind BoxOutput (ROI pooling / ROI align / the pooling
+ * that follows ROI align in the cascade nets) and mscnn_conv_desc.dyn_n take an optional DEVICE count: the launch is
+ * sized for the cap (N resp. R) and the kernel processes min(cap, *dyn) rows.  The reference knows R on the host at this
+ * point because its BoxOutput is host code (box_output_layer.cpp:201); here nothing waits for the device mid-forward. */
+MSCNN_API int mscnn_pool_forward_dyn(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H, int W,
+                           int C, int kernel, int stride, int mode, const int* dyn_n, void* stream);
+MSCNN_API int mscnn_roi_pool_multi_forward_dyn(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                     const float* rois, int R, int pooled_h, int pooled_w, float spatial_scale,
+                                     int num_variants, const float* pad_ratios, const int* out_channel_offsets,
+                                     void* y_hi, void* y_lo, int out_channels_total, const int* dyn_R, void* stream);
+MSCNN_API int mscnn_roi_align_forward_dyn(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                const float* rois, int R, int pooled_h, int pooled_w, float spatial_scale,
+                                float pad_ratio, void* y_hi, void* y_lo, int out_channels_total,
+                                int out_channel_offset, const int* dyn_R, void* stream);
 
 /* Stand-alone ReLU (in place) and channel Concat for planes / fp32 blobs.  mscnn_b200's Net fuses
  * ReLU into the producing convolution and Concat into ROIPooling; these serve unfused use.
@@ -413,6 +433,17 @@ MSCNN_API const float* mscnn_net_blob_device(void* net, const char* blob);
 MSCNN_API int mscnn_net_set_input_images(void* net, const char* blob, void* preprocess_plan, int N,
                                          const unsigned char* host_images);
 MSCNN_API int mscnn_net_forward(void* net, int from_layer, int to_layer); /* inclusive; to < 0 = last */
+/* mscnn_net_forward returns with the forward QUEUED on the stream: no layer waits for the device, not even BoxOutput,
+ * whose data-dependent row count R stays on the device for the layers behind it (mscnn_conv_desc.dyn_n and the *_dyn
+ * entries).  The blobs behind BoxOutput have cap rows until the host asks: every accessor of this facade that returns a
+ * shape or a value first waits for the 12-byte count and trims them to R (= mscnn_net_resolve_rows), which is the
+ * shape the reference reports (box_output_layer.cpp:201).
+ * mscnn_net_set_graph(net, 1): after one eager forward the launches of a whole forward are captured into a CUDA graph
+ * and replayed while input shapes, parameter versions, precision and stream stay the same (a non-default stream is
+ * required); mscnn_net_graph_replayed tells whether the last forward was a replay. */
+MSCNN_API int mscnn_net_resolve_rows(void* net);
+MSCNN_API int mscnn_net_set_graph(void* net, int on);
+MSCNN_API int mscnn_net_graph_replayed(void* net);
 MSCNN_API int mscnn_net_set_layer_timing(void* net, int on);
 MSCNN_API int mscnn_net_layer_times(void* net, float* ms);                 /* ms per layer, last forward */
 MSCNN_API int mscnn_net_num_proposals(void* net, int image);               /* image < 0: whole batch */

@@ -41,6 +41,7 @@ class ConvDesc(C.Structure):
         ("relu", c_int), ("out_mode", c_int),
         ("y_hi", c_void_p), ("y_lo", c_void_p), ("y_f32", c_void_p),
         ("pool_hi", c_void_p), ("pool_lo", c_void_p),
+        ("dyn_n", c_void_p),
     ]
 
 

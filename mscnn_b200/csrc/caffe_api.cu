@@ -192,7 +192,12 @@ void Blob<Dtype>::Reshape(const int num, const int channels, const int height, c
 template <typename Dtype>
 void Blob<Dtype>::Reshape(const vector<int>& shape) {  // blob.cpp:23-45: grow-only capacity
   CHECK_LE(shape.size(), (size_t)kMaxBlobAxes);
-  const bool same = (shape == shape_);
+  bool same = (shape == shape_);
+  // a trim along axis 0 keeps the leading rows of BOTH layouts valid (NCHW rows and NHWC planes are row-major in n):
+  // that is what Net::ResolveRows does to the blobs behind BoxOutput once the data-dependent row count is known
+  if (!same && shape.size() == shape_.size() && !shape.empty() && shape[0] <= shape_[0] &&
+      std::equal(shape.begin() + 1, shape.end(), shape_.begin() + 1))
+    same = true;
   count_ = 1;
   shape_.resize(shape.size());
   for (size_t i = 0; i < shape.size(); ++i) {

@@ -18,6 +18,17 @@
 
 namespace caffe {
 
+// mscnn_b200 extension: data-dependent row counts that stay on the device.  BoxOutput's number of proposals R is only
+// known after its kernels have run; the reference learns it on the host (its BoxOutput IS host code,
+// box_output_layer.cpp:201) and shapes every later blob with it.  Here a Net sizes those blobs for the cap
+// (N x max_nms_num rows), every layer behind BoxOutput reads R from device memory (`device_rows`: rows to process,
+// >= 1) and skips the rest, and the blob shapes are trimmed to R when the host next needs them (Net::ResolveRows).
+// `pending` = the blobs currently have cap rows and device_rows is authoritative.
+struct DynRows {
+  const int* device_rows;
+  bool pending;
+};
+
 template <typename Dtype>
 class CAFFE_API Layer {
  public:
@@ -62,6 +73,9 @@ class CAFFE_API Layer {
 
   vector<shared_ptr<Blob<Dtype> > >& blobs() { return blobs_; }
   const LayerParameter& layer_param() const { return layer_param_; }
+  // mscnn_b200 extension (set by Net for the layers behind a BoxOutput layer): see DynRows
+  void set_dyn_rows(const DynRows* d) { dyn_rows_ = d; }
+  const int* dyn_rows_device() const { return (dyn_rows_ && dyn_rows_->pending) ? dyn_rows_->device_rows : nullptr; }
   virtual inline const char* type() const { return ""; }
   virtual inline int ExactNumBottomBlobs() const { return -1; }
   virtual inline int MinBottomBlobs() const { return -1; }
@@ -75,6 +89,7 @@ class CAFFE_API Layer {
   LayerParameter layer_param_;
   Phase phase_;
   vector<shared_ptr<Blob<Dtype> > > blobs_;
+  const DynRows* dyn_rows_ = nullptr;
 
   virtual void Forward_cpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
     LOG(FATAL) << "mscnn_b200: layer " << layer_param_.name() << " (" << type()

@@ -224,6 +224,15 @@ class CAFFE_API BoxOutputLayer : public Layer<Dtype> {
   int max_rows_per_image() const {
     return (cfg_.max_post_nms_num > 0 && cfg_.max_post_nms_num < cfg_.max_nms_num) ? cfg_.max_post_nms_num : cfg_.max_nms_num;
   }
+  // Deferred rows (set by Net): Forward leaves the tops at cap rows and does NOT wait for the device; ResolveRows
+  // waits for the 12-byte copy of the counts and trims the tops.  Without it (a layer driven directly) Forward
+  // synchronises and trims itself, which is the reference's observable behaviour (box_output_layer.cpp:201).
+  void set_defer_rows(bool on) { defer_rows_ = on; }
+  const DynRows* dyn_rows() const { return &dyn_; }
+  bool rows_pending() const { return dyn_.pending; }
+  void ResolveRows(const vector<Blob<Dtype>*>& top);
+  // after a CUDA-graph replay of this layer's launches (Net::GraphForward): the counts are pending again
+  void RearmRows();
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
   mscnn_box_output_cfg cfg_;
@@ -234,6 +243,9 @@ class CAFFE_API BoxOutputLayer : public Layer<Dtype> {
   int* num_out_host_;
   int num_out_cap_;
   Blob<Dtype> scratch_score_;
+  bool defer_rows_ = false;
+  DynRows dyn_ = {nullptr, false};
+  cudaEvent_t rows_event_ = nullptr;
 };
 
 /// ROIPoolingLayer: roi_pooling_layer.cpp:22-139 with the MS-CNN pad_ratio extension.

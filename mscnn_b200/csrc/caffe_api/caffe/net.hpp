@@ -71,6 +71,20 @@ class CAFFE_API Net {
   void set_layer_timing(bool on) { time_layers_ = on; }
   const vector<float>& layer_times_ms() const { return layer_ms_; }
 
+  // mscnn_b200 extension: data-dependent rows (layer.hpp DynRows).  No layer waits for the device in the middle of a
+  // forward: the blobs behind BoxOutput keep cap rows while the kernels read the true count on the device.
+  // ResolveRows() waits for the count (a 12-byte copy issued right behind BoxOutput) and trims those blobs' shapes to
+  // what the reference reports (box_output_layer.cpp:201).  ForwardFromTo() calls it before returning unless
+  // set_lazy_rows(true): then the forward returns with everything merely queued and the host calls ResolveRows()
+  // when it next needs a shape (the C facade does so in every accessor).
+  void set_lazy_rows(bool on) { lazy_rows_ = on; }
+  void ResolveRows();
+  void ResolveRowsFor(const string& blob_name);  // only if that blob's shape depends on the pending count
+  // Capture the layers of ForwardFromTo(0, last) into a CUDA graph after one eager forward and replay it while
+  // nothing it depends on changed (blob shapes, parameter versions, precision, config epoch); off by default.
+  void set_graph_mode(bool on) { graph_mode_ = on; }
+  bool graph_replayed_last_forward() const { return graph_replayed_; }
+
  protected:
   void AppendTop(const NetParameter& param, const int layer_id, const int top_id,
                  set<string>* available_blobs, map<string, int>* blob_name_to_idx);
@@ -78,6 +92,8 @@ class CAFFE_API Net {
                    set<string>* available_blobs, map<string, int>* blob_name_to_idx);
   void FuseLayers();
   void FusePooling();
+  void MarkDynamicRows();
+  bool GraphForward(int start, int end);
 
   string name_;
   Phase phase_;
@@ -97,6 +113,13 @@ class CAFFE_API Net {
   vector<Blob<Dtype>*> net_output_blobs_;
   bool time_layers_;
   vector<float> layer_ms_;
+  int dyn_box_ = -1;            // index of the BoxOutput layer whose rows are deferred (-1: none / several)
+  vector<int> dyn_layers_;      // layers whose row count derives from it, in execution order
+  set<string> dyn_blob_names_;  // blobs whose row count derives from it
+  bool lazy_rows_ = false;
+  bool graph_mode_ = false, graph_replayed_ = false;
+  struct GraphState;
+  shared_ptr<GraphState> graph_;
   DISABLE_COPY_AND_ASSIGN(Net);
 };
 

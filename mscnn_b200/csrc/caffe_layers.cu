@@ -199,7 +199,8 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
     d.pad_h = pad_h_; d.pad_w = 0;
     d.out_mode = MSCNN_OUT_NHWC_F32;  // ... horizontal taps are columns of P
     d.y_f32 = P;
-    MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
+    d.dyn_n = this->dyn_rows_device();
+  MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
     MSCNN_CHECK(mscnn_head_gather(P, n_pad, head_bias_, top[0]->mutable_gpu_data(), N, H, W, num_output_, k, pad_h_,
                                   Caffe::stream()));
     return;
@@ -281,7 +282,8 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
     d.out_mode = MSCNN_OUT_NHWC_BF16;
     d.y_hi = y.hi;
     d.y_lo = y.lo;
-    MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
+    d.dyn_n = this->dyn_rows_device();
+  MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
     return;
   }
   if (first_path && conv1_mode != 3) {
@@ -343,6 +345,7 @@ void ConvolutionLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, co
     d.out_mode = MSCNN_OUT_NCHW_F32;  // narrow heads (LFCN_*): straight into the Caffe layout
     d.y_f32 = top[0]->mutable_gpu_data();
   }
+  d.dyn_n = this->dyn_rows_device();
   MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
 }
 
@@ -431,8 +434,8 @@ void PoolingLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const 
   const bool split = Caffe::split();
   typename Blob<Dtype>::Planes x = bottom[0]->planes(split);
   typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
-  MSCNN_CHECK(mscnn_pool_forward(x.hi, x.lo, y.hi, y.lo, x.n, x.h, x.w, x.cpad, kernel_, stride_, mode_,
-                                 Caffe::stream()));
+  MSCNN_CHECK(mscnn_pool_forward_dyn(x.hi, x.lo, y.hi, y.lo, x.n, x.h, x.w, x.cpad, kernel_, stride_, mode_,
+                                     this->dyn_rows_device(), Caffe::stream()));
 }
 
 // ---------------------------------------------------------------------------------- Split
@@ -587,6 +590,7 @@ void InnerProductLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, c
     d.out_mode = MSCNN_OUT_NCHW_F32;  // cls_pred / bbox_pred: [R][N_] fp32, the Caffe layout
     d.y_f32 = top[0]->mutable_gpu_data();
   }
+  d.dyn_n = this->dyn_rows_device();
   MSCNN_CHECK(mscnn_conv_forward(&d, Caffe::stream()));
 }
 
@@ -603,6 +607,21 @@ BoxOutputLayer<Dtype>::~BoxOutputLayer() {
   if (workspace_) cudaFree(workspace_);
   if (num_out_dev_) cudaFree(num_out_dev_);
   if (num_out_host_) cudaFreeHost(num_out_host_);
+  if (rows_event_) cudaEventDestroy(rows_event_);
+}
+template <typename Dtype>
+void BoxOutputLayer<Dtype>::ResolveRows(const vector<Blob<Dtype>*>& top) {
+  if (!dyn_.pending) return;
+  CUDA_CHECK(cudaEventSynchronize(rows_event_));
+  dyn_.pending = false;
+  const int rows = num_out_host_[0];
+  top[0]->Reshape(rows, 5, 1, 1);
+  if (output_proposal_with_score_) top[1]->Reshape(rows, 6, 1, 1);
+}
+template <typename Dtype>
+void BoxOutputLayer<Dtype>::RearmRows() {
+  CUDA_CHECK(cudaEventRecord(rows_event_, Caffe::stream()));
+  dyn_.pending = true;
 }
 template <typename Dtype>
 void BoxOutputLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
@@ -640,7 +659,9 @@ void BoxOutputLayer<Dtype>::LayerSetUp(const vector<Blob<Dtype>*>& bottom, const
 }
 template <typename Dtype>
 void BoxOutputLayer<Dtype>::Reshape(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top) {
-  // "dummy reshape" (box_output_layer.cpp:29-36); the real shape is data dependent
+  // "dummy reshape" (box_output_layer.cpp:29-36); the real shape is data dependent.  Rows still pending from the
+  // last Forward (Net::ResolveRows re-runs Reshape down the net) keep their cap shape until resolved.
+  if (dyn_.pending) return;
   top[0]->Reshape(1, 5, 1, 1);
   if (output_proposal_with_score_) top[1]->Reshape(1, 6, 1, 1);
 }
@@ -669,7 +690,10 @@ void BoxOutputLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, cons
     CUDA_CHECK(cudaMalloc(&num_out_dev_, sizeof(int) * (2 + N)));
     CUDA_CHECK(cudaMallocHost(&num_out_host_, sizeof(int) * (2 + N)));
     num_out_cap_ = 2 + N;
+    dyn_.device_rows = num_out_dev_;  // [0] = rows in the top blobs (>= 1)
   }
+  if (!rows_event_) CUDA_CHECK(cudaEventCreateWithFlags(&rows_event_, cudaEventDisableTiming));
+  dyn_.pending = false;  // a new Forward supersedes counts nobody asked for
   // Size the tops for the cap, let the kernels write in place, then shrink to the true row
   // count (Blob::Reshape never reallocates when shrinking, blob.cpp:40-44).
   const int cap = N * cfg_.max_nms_num;
@@ -682,10 +706,12 @@ void BoxOutputLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, cons
                                        num_out_dev_, Caffe::stream()));
   CUDA_CHECK(cudaMemcpyAsync(num_out_host_, num_out_dev_, sizeof(int) * (2 + N), cudaMemcpyDeviceToHost,
                              Caffe::stream()));
-  CUDA_CHECK(cudaStreamSynchronize(Caffe::stream()));
-  const int rows = num_out_host_[0];
-  top[0]->Reshape(rows, 5, 1, 1);
-  if (output_proposal_with_score_) top[1]->Reshape(rows, 6, 1, 1);
+  cudaStreamCaptureStatus capturing = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(Caffe::stream(), &capturing);
+  if (capturing == cudaStreamCaptureStatusNone)  // under capture the Net re-arms after the graph launch (RearmRows)
+    CUDA_CHECK(cudaEventRecord(rows_event_, Caffe::stream()));
+  dyn_.pending = true;  // tops have `cap` rows; the true count is in num_out_dev_[0] (and soon in num_out_host_[0])
+  if (!defer_rows_) ResolveRows(top);
 }
 
 // ----------------------------------------------------------------------------- ROIPooling
@@ -737,13 +763,15 @@ void ROIPoolingLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, con
         sb->mark_done_by_leader();
       }
     }
-    MSCNN_CHECK(mscnn_roi_pool_multi_forward(x.hi, x.lo, x.n, x.h, x.w, x.cpad, rois, R, pooled_height_,
-                                             pooled_width_, spatial_scale_, nv, ratios, offs, y.hi, y.lo, y.cpad,
-                                             Caffe::stream()));
+    MSCNN_CHECK(mscnn_roi_pool_multi_forward_dyn(x.hi, x.lo, x.n, x.h, x.w, x.cpad, rois, R, pooled_height_,
+                                                 pooled_width_, spatial_scale_, nv, ratios, offs, y.hi, y.lo, y.cpad,
+                                                 this->dyn_rows_device(), Caffe::stream()));
   } else {
     typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
-    MSCNN_CHECK(mscnn_roi_pool_forward(x.hi, x.lo, x.n, x.h, x.w, x.cpad, rois, R, pooled_height_, pooled_width_,
-                                       spatial_scale_, pad_ratio_, y.hi, y.lo, y.cpad, 0, Caffe::stream()));
+    const int off0 = 0;
+    MSCNN_CHECK(mscnn_roi_pool_multi_forward_dyn(x.hi, x.lo, x.n, x.h, x.w, x.cpad, rois, R, pooled_height_,
+                                                 pooled_width_, spatial_scale_, 1, &pad_ratio_, &off0, y.hi, y.lo,
+                                                 y.cpad, this->dyn_rows_device(), Caffe::stream()));
   }
 }
 
@@ -772,9 +800,9 @@ void ROIAlignLayer<Dtype>::Forward_gpu(const vector<Blob<Dtype>*>& bottom, const
   const bool split = Caffe::split();
   typename Blob<Dtype>::Planes x = bottom[0]->planes(split);
   typename Blob<Dtype>::Planes y = top[0]->mutable_planes(split);
-  MSCNN_CHECK(mscnn_roi_align_forward(x.hi, x.lo, x.n, x.h, x.w, x.cpad, bottom[1]->gpu_data(), bottom[1]->num(),
-                                      pooled_height_, pooled_width_, spatial_scale_, pad_ratio_, y.hi, y.lo,
-                                      y.cpad, 0, Caffe::stream()));
+  MSCNN_CHECK(mscnn_roi_align_forward_dyn(x.hi, x.lo, x.n, x.h, x.w, x.cpad, bottom[1]->gpu_data(), bottom[1]->num(),
+                                          pooled_height_, pooled_width_, spatial_scale_, pad_ratio_, y.hi, y.lo,
+                                          y.cpad, 0, this->dyn_rows_device(), Caffe::stream()));
 }
 
 // ----------------------------------------------------------------------------- DecodeBBox

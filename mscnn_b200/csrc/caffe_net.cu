@@ -8,6 +8,8 @@
 
 #include "caffe/layers/mscnn_layers.hpp"
 #include "caffe/net.hpp"
+#include "config.h"
+#include "launch_count.h"
 #include "proto_text.hpp"
 
 namespace caffe {
@@ -159,6 +161,48 @@ void Net<Dtype>::Init(const NetParameter& in_param) {
   if (!std::getenv("MSCNN_NO_FUSION")) {
     FuseLayers();
     if (!std::getenv("MSCNN_NO_POOL_FUSION")) FusePooling();
+  }
+  if (!std::getenv("MSCNN_SYNC_ROWS")) MarkDynamicRows();
+}
+
+// Layers whose row count is BoxOutput's data-dependent R (transitively: any layer with a bottom blob in the set puts
+// its tops into the set).  With exactly one BoxOutput layer in the net its rows are deferred (layer.hpp DynRows).
+template <typename Dtype>
+void Net<Dtype>::MarkDynamicRows() {
+  const int L = (int)layers_.size();
+  int box = -1, boxes = 0;
+  for (int i = 0; i < L; ++i)
+    if (dynamic_cast<BoxOutputLayer<Dtype>*>(layers_[i].get())) { box = i; ++boxes; }
+  if (boxes != 1) return;
+  BoxOutputLayer<Dtype>* b = static_cast<BoxOutputLayer<Dtype>*>(layers_[box].get());
+  set<int> dyn_blobs(top_id_vecs_[box].begin(), top_id_vecs_[box].end());
+  for (int i = box + 1; i < L; ++i) {
+    bool hit = false;
+    for (size_t k = 0; k < bottom_id_vecs_[i].size(); ++k) hit |= dyn_blobs.count(bottom_id_vecs_[i][k]) > 0;
+    if (!hit) continue;
+    dyn_blobs.insert(top_id_vecs_[i].begin(), top_id_vecs_[i].end());
+    layers_[i]->set_dyn_rows(b->dyn_rows());
+    dyn_layers_.push_back(i);
+  }
+  b->set_defer_rows(true);
+  dyn_box_ = box;
+  for (set<int>::iterator it = dyn_blobs.begin(); it != dyn_blobs.end(); ++it) dyn_blob_names_.insert(blob_names_[*it]);
+}
+
+template <typename Dtype>
+void Net<Dtype>::ResolveRowsFor(const string& blob_name) {
+  if (dyn_box_ >= 0 && dyn_blob_names_.count(blob_name)) ResolveRows();
+}
+
+template <typename Dtype>
+void Net<Dtype>::ResolveRows() {
+  if (dyn_box_ < 0) return;
+  BoxOutputLayer<Dtype>* b = static_cast<BoxOutputLayer<Dtype>*>(layers_[dyn_box_].get());
+  if (!b->rows_pending()) return;
+  b->ResolveRows(top_vecs_[dyn_box_]);
+  for (size_t k = 0; k < dyn_layers_.size(); ++k) {
+    const int i = dyn_layers_[k];
+    layers_[i]->Reshape(bottom_vecs_[i], top_vecs_[i]);  // shrinking never reallocates (blob.cpp:40-44)
   }
 }
 
@@ -334,10 +378,83 @@ void Net<Dtype>::FusePooling() {
   }
 }
 
+// ---- CUDA graph replay of the whole forward (set_graph_mode) ----------------------------------------------------
+// The forward of a fixed-shape net is the same ~50 launches every time; with deferred rows (layer.hpp DynRows) no layer
+// talks to the host in between, so the launches of ForwardFromTo(0, last) are captured once (after one eager forward
+// that did every allocation and weight packing) and replayed with a single cudaGraphLaunch.  What a launch depends on
+// is folded into a signature: input shapes, parameter versions, precision, stream, config epoch; any change drops the
+// graph.  Host-side layer state is identical after every forward of a fixed-shape net, so a replay leaves it alone,
+// except BoxOutput's pending row count, which is re-armed.
+template <typename Dtype>
+struct Net<Dtype>::GraphState {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  std::string signature;
+  int warm = 0;
+  unsigned long long kernel_nodes = 0;
+  ~GraphState() {
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+  }
+};
+
+template <typename Dtype>
+bool Net<Dtype>::GraphForward(int start, int end) {
+  graph_replayed_ = false;
+  cudaStream_t stream = Caffe::stream();
+  if (!graph_mode_ || time_layers_ || start != 0 || end != (int)layers_.size() - 1 || stream == nullptr) return false;
+  std::ostringstream sig;
+  sig << (void*)stream << "|" << (int)Caffe::precision() << "|" << mscnn::config().epoch << "|";
+  for (size_t i = 0; i < net_input_blobs_.size(); ++i) sig << net_input_blobs_[i]->shape_string() << ";";
+  unsigned long versions = 0;
+  for (size_t i = 0; i < layers_.size(); ++i)
+    for (size_t j = 0; j < layers_[i]->blobs().size(); ++j) versions += layers_[i]->blobs()[j]->version() * (unsigned long)(31 * i + j + 1);
+  sig << versions;
+  if (!graph_ || graph_->signature != sig.str()) {
+    graph_.reset(new GraphState());
+    graph_->signature = sig.str();
+  }
+  GraphState& g = *graph_;
+  if (g.warm == 0) {  // one eager forward first: allocations and weight packing must not happen under capture
+    g.warm = 1;
+    return false;
+  }
+  BoxOutputLayer<Dtype>* box = dyn_box_ >= 0 ? static_cast<BoxOutputLayer<Dtype>*>(layers_[dyn_box_].get()) : nullptr;
+  if (!g.exec) {
+    if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    for (int i = start; i <= end; ++i) layers_[i]->Forward(bottom_vecs_[i], top_vecs_[i]);
+    cudaGraph_t graph = nullptr;
+    CUDA_CHECK(cudaStreamEndCapture(stream, &graph));
+    g.graph = graph;
+    CUDA_CHECK(cudaGraphInstantiate(&g.exec, graph, 0));
+    size_t n = 0;
+    CUDA_CHECK(cudaGraphGetNodes(graph, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (n) CUDA_CHECK(cudaGraphGetNodes(graph, nodes.data(), &n));
+    for (size_t k = 0; k < n; ++k) {
+      cudaGraphNodeType t;
+      if (cudaGraphNodeGetType(nodes[k], &t) == cudaSuccess && t == cudaGraphNodeTypeKernel) ++g.kernel_nodes;
+    }
+  } else {
+    mscnn::g_kernel_launches.fetch_add(g.kernel_nodes, std::memory_order_relaxed);  // the capture counted its own
+  }
+  CUDA_CHECK(cudaGraphLaunch(g.exec, stream));
+  if (box) box->RearmRows();
+  graph_replayed_ = true;
+  return true;
+}
+
 template <typename Dtype>
 Dtype Net<Dtype>::ForwardFromTo(int start, int end) {
   CHECK_GE(start, 0);
   CHECK_LT(end, (int)layers_.size());
+  if (GraphForward(start, end)) {
+    if (!lazy_rows_) ResolveRows();
+    return Dtype(0);
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (time_layers_) {
     CUDA_CHECK(cudaEventCreate(&e0));
@@ -356,6 +473,7 @@ Dtype Net<Dtype>::ForwardFromTo(int start, int end) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
   }
+  if (!lazy_rows_) ResolveRows();
   return Dtype(0);
 }
 
@@ -434,7 +552,7 @@ struct Reader {
   }
 };
 
-static void parse_blob(Reader r, BlobProto* b) {
+static void parse_blob(Reader r, BlobProto* b, bool* ok) {
   while (!r.done()) {
     const uint64_t key = r.varint();
     const int field = (int)(key >> 3), wt = (int)(key & 7);
@@ -459,7 +577,8 @@ static void parse_blob(Reader r, BlobProto* b) {
         memcpy(&v, d.p + 4 * i, 4);
         b->add_data(v);
       }
-    } else if (field == 5 && wt == 5) {
+    } else if (field == 5 && wt == 5) {  // non-packed float
+      if (r.end - r.p < 4) { r.ok = false; return; }
       float v;
       memcpy(&v, r.p, 4);
       r.p += 4;
@@ -481,7 +600,33 @@ static void parse_blob(Reader r, BlobProto* b) {
     } else {
       r.skip(wt);
     }
+    if (!r.ok) { *ok = false; return; }
   }
+}
+
+// One layer message.  LayerParameter: name = 1, type = 2, blobs = 7 (caffe.proto:310-330); the legacy
+// V1LayerParameter (NetParameter.layers = 2): name = 4, blobs = 6 (caffe.proto:1100-1150) -- the reference upgrades
+// such files when it loads them (upgrade_proto.cpp:NetNeedsV1ToV2Upgrade); only names and blobs matter here.
+static bool parse_layer(Reader l, LayerParameter* lp, int f_name, int f_type, int f_blobs) {
+  while (!l.done()) {
+    const uint64_t k2 = l.varint();
+    const int f2 = (int)(k2 >> 3), w2 = (int)(k2 & 7);
+    if (f2 == f_name && w2 == 2) {
+      Reader s = l.sub();
+      lp->set_name(std::string((const char*)s.p, (size_t)(s.end - s.p)));
+    } else if (f2 == f_type && w2 == 2) {
+      Reader s = l.sub();
+      lp->set_type(std::string((const char*)s.p, (size_t)(s.end - s.p)));
+    } else if (f2 == f_blobs && w2 == 2) {
+      bool ok = true;
+      parse_blob(l.sub(), lp->add_blobs(), &ok);
+      if (!ok) return false;
+    } else {
+      l.skip(w2);
+    }
+    if (!l.ok) return false;
+  }
+  return true;
 }
 
 static bool parse_net(const std::string& bytes, NetParameter* np) {
@@ -490,24 +635,9 @@ static bool parse_net(const std::string& bytes, NetParameter* np) {
     const uint64_t key = r.varint();
     const int field = (int)(key >> 3), wt = (int)(key & 7);
     if (field == 100 && wt == 2) {
-      Reader l = r.sub();
-      LayerParameter* lp = np->add_layer();
-      while (!l.done()) {
-        const uint64_t k2 = l.varint();
-        const int f2 = (int)(k2 >> 3), w2 = (int)(k2 & 7);
-        if (f2 == 1 && w2 == 2) {
-          Reader s = l.sub();
-          lp->set_name(std::string((const char*)s.p, (size_t)(s.end - s.p)));
-        } else if (f2 == 2 && w2 == 2) {
-          Reader s = l.sub();
-          lp->set_type(std::string((const char*)s.p, (size_t)(s.end - s.p)));
-        } else if (f2 == 7 && w2 == 2) {
-          parse_blob(l.sub(), lp->add_blobs());
-        } else {
-          l.skip(w2);
-        }
-        if (!l.ok) return false;
-      }
+      if (!parse_layer(r.sub(), np->add_layer(), 1, 2, 7)) return false;
+    } else if (field == 2 && wt == 2) {  // V1LayerParameter (type is an enum there: not needed for the copy)
+      if (!parse_layer(r.sub(), np->add_layer(), 4, -1, 6)) return false;
     } else if (field == 1 && wt == 2) {
       Reader s = r.sub();
       np->set_name(std::string((const char*)s.p, (size_t)(s.end - s.p)));
@@ -528,6 +658,11 @@ void Net<Dtype>::CopyTrainedLayersFrom(const string trained_filename) {
   ss << in.rdbuf();
   NetParameter param;
   CHECK(wire::parse_net(ss.str(), &param)) << "malformed caffemodel " << trained_filename;
+  int matched = 0;
+  for (int i = 0; i < param.layer_size(); ++i) matched += layer_names_index_.count(param.layer(i).name()) ? 1 : 0;
+  if (matched == 0)
+    LOG(WARNING) << trained_filename << ": none of its " << param.layer_size() << " layers matches a layer of this net "
+                 << "by name; the net keeps its current parameters";
   CopyTrainedLayersFrom(param);
 }
 

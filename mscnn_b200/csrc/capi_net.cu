@@ -24,7 +24,7 @@ struct NetHandle {
   // of the NEXT forward's input against the layers of the CURRENT forward that still read the blob.
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t input_ready = nullptr, inputs_consumed = nullptr;
-  bool pending_input = false, consumed_valid = false;
+  bool pending_input = false, consumed_valid = false, graph_mode = false;
   int pending_consumer = -1;
   ~NetHandle() {
     if (det_ws) cudaFree(det_ws);
@@ -82,6 +82,9 @@ void* mscnn_net_create(const char* prototxt, int is_path) {
   for (size_t i = 0; i < h->net->layers().size(); ++i)
     if (caffe::BoxOutputLayer<float>* b = dynamic_cast<caffe::BoxOutputLayer<float>*>(h->net->layers()[i].get()))
       h->box = b;
+  // mscnn_net_forward returns with the forward merely queued; every accessor below that needs a shape or a value on
+  // the host resolves the data-dependent row count first (Net::ResolveRows)
+  h->net->set_lazy_rows(true);
   return h;
 }
 void mscnn_net_destroy(void* h) { delete H(h); }
@@ -174,20 +177,24 @@ const char* mscnn_net_output_name(void* h, int i) {
   return H(h)->net->blob_names()[H(h)->net->output_blob_indices()[i]].c_str();
 }
 int mscnn_net_blob_shape(void* h, const char* name, int* shape4) {
+  H(h)->net->ResolveRowsFor(name);
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   return fill_shape(H(h)->net->blob_by_name(name)->shape(), shape4);
 }
 int mscnn_net_reshape_blob(void* h, const char* name, int n, int c, int hh, int w) {
+  H(h)->net->ResolveRowsFor(name);
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   H(h)->net->blob_by_name(name)->Reshape(n, c, hh, w);
   return MSCNN_OK;
 }
 int mscnn_net_reshape(void* h) {
+  H(h)->net->ResolveRows();
   H(h)->net->Reshape();
   return MSCNN_OK;
 }
 // host -> blob (pinned staging inside SyncedMemory; the H2D copy is issued on the net stream)
 int mscnn_net_set_blob(void* h, const char* name, const float* host, long count) {
+  H(h)->net->ResolveRowsFor(name);
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   Blob<float>* b = H(h)->net->blob_by_name(name).get();
   if (b->count() != count) return MSCNN_ERR_INVALID;
@@ -199,6 +206,7 @@ int mscnn_net_set_blob(void* h, const char* name, const float* host, long count)
 }
 // uint8 host images -> device pre-processing -> input blob (run_mscnn_detection.m:64-69 on the device)
 int mscnn_net_set_input_images(void* h, const char* name, void* plan, int N, const unsigned char* host_images) {
+  H(h)->net->ResolveRowsFor(name);
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   mscnn_preprocess_desc d;
   if (mscnn_preprocess_get_desc(plan, &d) != MSCNN_OK) return MSCNN_ERR_INVALID;
@@ -208,6 +216,7 @@ int mscnn_net_set_input_images(void* h, const char* name, void* plan, int N, con
   return mscnn_preprocess_forward_host(plan, N, host_images, b->mutable_gpu_data(), Caffe::stream());
 }
 int mscnn_net_set_blob_device(void* h, const char* name, const float* dev, long count) {
+  H(h)->net->ResolveRowsFor(name);
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   Blob<float>* b = H(h)->net->blob_by_name(name).get();
   if (b->count() != count) return MSCNN_ERR_INVALID;
@@ -218,6 +227,7 @@ int mscnn_net_set_blob_device(void* h, const char* name, const float* dev, long 
              : MSCNN_ERR_CUDA;
 }
 int mscnn_net_get_blob(void* h, const char* name, float* host, long count) {
+  H(h)->net->ResolveRowsFor(name);
   if (!H(h)->net->has_blob(name)) return MSCNN_ERR_INVALID;
   Blob<float>* b = H(h)->net->blob_by_name(name).get();
   if (b->count() != count) return MSCNN_ERR_INVALID;
@@ -227,6 +237,7 @@ int mscnn_net_get_blob(void* h, const char* name, float* host, long count) {
   return cudaStreamSynchronize(Caffe::stream()) == cudaSuccess ? MSCNN_OK : MSCNN_ERR_CUDA;
 }
 const float* mscnn_net_blob_device(void* h, const char* name) {
+  H(h)->net->ResolveRowsFor(name);
   if (!H(h)->net->has_blob(name)) return nullptr;
   return H(h)->net->blob_by_name(name)->gpu_data();
 }
@@ -244,6 +255,13 @@ int mscnn_net_forward(void* h, int from, int to) {
   }
   if (!nh->copy_stream) {  // asynchronous uploads never used on this net: nothing to order
     net->ForwardFromTo(from, to);
+    return MSCNN_OK;
+  }
+  if (nh->graph_mode && from == 0 && to == (int)net->layers().size() - 1) {
+    // graph replay: one launch for the whole forward; the input blob is free again when it has finished
+    net->ForwardFromTo(from, to);
+    if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess) return MSCNN_ERR_CUDA;
+    nh->consumed_valid = true;
     return MSCNN_OK;
   }
   // Every forward records the point after which the input blob may be overwritten by the next asynchronous upload:
@@ -264,6 +282,7 @@ int mscnn_net_forward(void* h, int from, int to) {
 // forward in flight that read this blob have run, and the next mscnn_net_forward waits for it on the device.
 // `host` must stay valid (and should be pinned) until that forward has been issued.
 int mscnn_net_set_blob_async(void* h, const char* name, const float* host, long count) {
+  H(h)->net->ResolveRowsFor(name);
   NetHandle* nh = H(h);
   Net<float>* net = nh->net.get();
   if (!net->has_blob(name)) return MSCNN_ERR_INVALID;
@@ -301,6 +320,18 @@ int mscnn_net_set_blob_async(void* h, const char* name, const float* host, long 
   nh->pending_consumer = consumer;
   return MSCNN_OK;
 }
+// CUDA-graph replay of whole forwards (Net::set_graph_mode): off by default
+int mscnn_net_set_graph(void* h, int on) {
+  H(h)->graph_mode = on != 0;
+  H(h)->net->set_graph_mode(on != 0);
+  return MSCNN_OK;
+}
+int mscnn_net_graph_replayed(void* h) { return H(h)->net->graph_replayed_last_forward() ? 1 : 0; }
+// wait for the data-dependent row count of the last forward and trim the blob shapes (every accessor does this)
+int mscnn_net_resolve_rows(void* h) {
+  H(h)->net->ResolveRows();
+  return MSCNN_OK;
+}
 int mscnn_net_set_layer_timing(void* h, int on) {
   H(h)->net->set_layer_timing(on != 0);
   return MSCNN_OK;
@@ -312,6 +343,7 @@ int mscnn_net_layer_times(void* h, float* ms) {
 }
 // proposals of the last forward: total and per image (host values read back by BoxOutput)
 int mscnn_net_num_proposals(void* h, int image) {
+  H(h)->net->ResolveRows();
   if (!H(h)->box) return MSCNN_ERR_INVALID;
   return image < 0 ? H(h)->box->num_proposals() : H(h)->box->image_proposals(image);
 }

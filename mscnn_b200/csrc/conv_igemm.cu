@@ -88,6 +88,7 @@ struct IgemmParams {
   int mt;             // M sub-tiles (128 pixels each) per CTA tile: one weight tile feeds mt activation tiles
   int tmem_cols;      // 2 * mt * BLOCK_N rounded to a power of two >= 32
   const float* bias;  // [Cout_pad]
+  const int* dyn_n;   // optional device count: process min(*dyn_n, out_n) images only (mscnn_conv_desc.dyn_n)
   float* out_f32;     // NCHW fp32 (out_mode 1)
   int out_n, out_c, out_h, out_w;
   int out_ld;         // row length of the pixel-major fp32 output (MSCNN_OUT_NHWC_F32)
@@ -192,8 +193,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi,
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
-  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_n;
-  // the host guarantees m_tiles % MT == 0; in vpool mode the tile grid is already one of row pairs
+  // data-dependent batch size: every role derives the same tile count from the device-side count
+  int tiles_n = p.tiles_n;
+  if (p.dyn_n != nullptr) {
+    int n_eff = *p.dyn_n;
+    n_eff = n_eff < 0 ? 0 : (n_eff > p.out_n ? p.out_n : n_eff);
+    tiles_n = (n_eff + p.box_n - 1) / p.box_n;
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * tiles_n;
+  // the host guarantees m_tiles % MT == 0 (MT = 1 with dyn_n); in vpool mode the tile grid is already one of row pairs
   const int total_tiles = PAIR ? ((m_tiles + 1) / 2) * p.n_tiles
                           : p.vpool ? m_tiles * p.n_tiles : (m_tiles / MT) * p.n_tiles;
   // pair mode: `tile` counts PAIR tiles, a cluster strides over them; this CTA's M tile is 2 * (tile / n_tiles) + rank
@@ -941,7 +949,7 @@ struct ConvPlan {
 };
 
 struct PlanKey {
-  const void* ptr[10];
+  const void* ptr[11];
   int v[15];
   bool operator==(const PlanKey& o) const { return memcmp(this, &o, sizeof(PlanKey)) == 0; }
 };
@@ -974,7 +982,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
   if (cudaGetDevice(&device) != cudaSuccess) return MSCNN_ERR_CUDA;
   PlanKey key;
   memset(&key, 0, sizeof(key));
-  const void* ptrs[10] = {d->x_hi, d->x_lo, d->w_hi, d->w_lo, d->bias, d->y_hi, d->y_lo, d->y_f32, d->pool_hi, d->pool_lo};
+  const void* ptrs[11] = {d->x_hi, d->x_lo, d->w_hi, d->w_lo, d->bias, d->y_hi, d->y_lo, d->y_f32, d->pool_hi, d->pool_lo, d->dyn_n};
   memcpy(key.ptr, ptrs, sizeof(ptrs));
   const int vals[15] = {d->N, d->H, d->W, d->C, d->Cout, d->Cout_pad, d->KH, d->KW, d->pad_h, d->pad_w, d->relu,
                         d->out_mode, device, static_cast<int>(config().epoch), 0};
@@ -1061,6 +1069,7 @@ static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan) {
   if (pool && p.store_full && p.has_lo_out && !d->y_lo) return MSCNN_ERR_INVALID;
   if (pool && p.has_lo_out && !d->pool_lo) return MSCNN_ERR_INVALID;
   p.bias = d->bias;
+  p.dyn_n = d->dyn_n;
   p.out_f32 = d->y_f32;
   p.out_n = d->N;
   p.out_c = d->Cout;
@@ -1086,6 +1095,7 @@ static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan) {
   if (BN <= 64) mt = 4;
   else if (BN == 128) mt = 2;
   if (cfg.mt > 0) mt = cfg.mt;
+  if (d->dyn_n) mt = 1;  // the tile count is only known on the device: no grouping of M sub-tiles
   if (mt > kMaxMt) mt = kMaxMt;
   if (mt < 1) mt = 1;
   while (mt > 1 && (2 * mt * BN * acc_mul > 512 || m_tiles_total % mt != 0 || m_tiles_total / mt * p.n_tiles < mscnn_sm_count())) mt >>= 1;

@@ -66,8 +66,9 @@ __device__ __forceinline__ void store8(__nv_bfloat16* hi, __nv_bfloat16* lo, siz
 // window size (pad 0 => pool_size = (hend-hstart)*(wend-wstart), :196-203).
 __global__ void pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
                             __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int N, int H,
-                            int W, int C, int Ho, int Wo, int k, int s, int mode) {
+                            int W, int C, int Ho, int Wo, int k, int s, int mode, const int* __restrict__ dyn_n) {
   const int cg = C / 8;
+  if (dyn_n) N = max(0, min(N, *dyn_n));  // data-dependent row count (mscnn_pool_forward_dyn)
   const size_t total = (size_t)N * Ho * Wo * cg;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -185,10 +186,12 @@ __device__ __forceinline__ void roi_pool_window(const uint4* __restrict__ xh4, c
 __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
                                 const float* __restrict__ rois, int R, int N, int H, int W, int C,
                                 int PH, int PW, float scale, const RoiVariants var,
-                                __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int Ctot) {
+                                __nv_bfloat16* __restrict__ yh, __nv_bfloat16* __restrict__ yl, int Ctot,
+                                const int* __restrict__ dyn_R) {
   const int cg = C / 8;
   const int lane = threadIdx.x & 31;
   const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
+  if (dyn_R) R = max(0, min(R, *dyn_R));  // data-dependent ROI count (mscnn_roi_pool_multi_forward_dyn)
   const size_t bins = (size_t)R * PH * PW;
   const uint4* xh4 = reinterpret_cast<const uint4*>(xh);
   const uint4* xl4 = reinterpret_cast<const uint4*>(xl);
@@ -240,11 +243,12 @@ __global__ void roi_pool_kernel(const __nv_bfloat16* __restrict__ xh, const __nv
 __global__ void roi_align_kernel(const __nv_bfloat16* __restrict__ xh, const __nv_bfloat16* __restrict__ xl,
                                  const float* __restrict__ rois, int R, int N, int H, int W, int C, int PH,
                                  int PW, float scale, float pad_ratio, __nv_bfloat16* __restrict__ yh,
-                                 __nv_bfloat16* __restrict__ yl, int Ctot, int c_off) {
+                                 __nv_bfloat16* __restrict__ yl, int Ctot, int c_off, const int* __restrict__ dyn_R) {
   const int cg = C / 8;
   const int GH = PH + 1, GW = PW + 1;
   const int lane = threadIdx.x & 31;
   const size_t warps_total = (size_t)gridDim.x * (blockDim.x >> 5);
+  if (dyn_R) R = max(0, min(R, *dyn_R));
   const size_t points = (size_t)R * GH * GW;
   for (size_t pt = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pt < points; pt += warps_total) {
     const int pw = pt % GW;
@@ -403,8 +407,8 @@ static int grid_for(size_t total, int threads) {
 
 using namespace mscnn;
 
-extern "C" int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H,
-                                  int W, int C, int kernel, int stride, int mode, void* stream) {
+extern "C" int mscnn_pool_forward_dyn(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H,
+                                      int W, int C, int kernel, int stride, int mode, const int* dyn_n, void* stream) {
   if (!x_hi || !y_hi || N <= 0 || H <= 0 || W <= 0 || C % 8 || kernel <= 0 || stride <= 0)
     return MSCNN_ERR_INVALID;
   if ((x_lo == nullptr) != (y_lo == nullptr)) return MSCNN_ERR_INVALID;
@@ -416,15 +420,20 @@ extern "C" int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi
   mscnn::note_launch();
   pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, N,
-      H, W, C, Ho, Wo, kernel, stride, mode);
+      H, W, C, Ho, Wo, kernel, stride, mode, dyn_n);
   return launch_check("pool");
 }
 
-extern "C" int mscnn_roi_pool_multi_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
-                                            const float* rois, int R, int pooled_h, int pooled_w,
-                                            float spatial_scale, int num_variants, const float* pad_ratios,
-                                            const int* out_channel_offsets, void* y_hi, void* y_lo,
-                                            int out_channels_total, void* stream) {
+extern "C" int mscnn_pool_forward(const void* x_hi, const void* x_lo, void* y_hi, void* y_lo, int N, int H,
+                                  int W, int C, int kernel, int stride, int mode, void* stream) {
+  return mscnn_pool_forward_dyn(x_hi, x_lo, y_hi, y_lo, N, H, W, C, kernel, stride, mode, nullptr, stream);
+}
+
+extern "C" int mscnn_roi_pool_multi_forward_dyn(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                                const float* rois, int R, int pooled_h, int pooled_w,
+                                                float spatial_scale, int num_variants, const float* pad_ratios,
+                                                const int* out_channel_offsets, void* y_hi, void* y_lo,
+                                                int out_channels_total, const int* dyn_R, void* stream) {
   if (!x_hi || !y_hi || !rois || !pad_ratios || !out_channel_offsets || N <= 0 || C % 8 || R < 0 ||
       pooled_h <= 0 || pooled_w <= 0 || out_channels_total % 8 || num_variants < 1 || num_variants > 4)
     return MSCNN_ERR_INVALID;
@@ -441,8 +450,18 @@ extern "C" int mscnn_roi_pool_multi_forward(const void* x_hi, const void* x_lo, 
   mscnn::note_launch();
   roi_pool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, rois, R, N, H, W, C, pooled_h, pooled_w,
-      spatial_scale, var, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total);
+      spatial_scale, var, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total, dyn_R);
   return launch_check("roi_pool");
+}
+
+extern "C" int mscnn_roi_pool_multi_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                            const float* rois, int R, int pooled_h, int pooled_w,
+                                            float spatial_scale, int num_variants, const float* pad_ratios,
+                                            const int* out_channel_offsets, void* y_hi, void* y_lo,
+                                            int out_channels_total, void* stream) {
+  return mscnn_roi_pool_multi_forward_dyn(x_hi, x_lo, N, H, W, C, rois, R, pooled_h, pooled_w, spatial_scale,
+                                          num_variants, pad_ratios, out_channel_offsets, y_hi, y_lo, out_channels_total,
+                                          nullptr, stream);
 }
 
 extern "C" int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
@@ -453,10 +472,11 @@ extern "C" int mscnn_roi_pool_forward(const void* x_hi, const void* x_lo, int N,
                                       &pad_ratio, &out_channel_offset, y_hi, y_lo, out_channels_total, stream);
 }
 
-extern "C" int mscnn_roi_align_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
-                                       const float* rois, int R, int pooled_h, int pooled_w,
-                                       float spatial_scale, float pad_ratio, void* y_hi, void* y_lo,
-                                       int out_channels_total, int out_channel_offset, void* stream) {
+extern "C" int mscnn_roi_align_forward_dyn(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                           const float* rois, int R, int pooled_h, int pooled_w,
+                                           float spatial_scale, float pad_ratio, void* y_hi, void* y_lo,
+                                           int out_channels_total, int out_channel_offset, const int* dyn_R,
+                                           void* stream) {
   if (!x_hi || !y_hi || !rois || N <= 0 || H <= 0 || W <= 0 || C % 8 || R < 0 || pooled_h <= 0 || pooled_w <= 0 ||
       out_channels_total % 8 || out_channel_offset % 8 || out_channel_offset + C > out_channels_total)
     return MSCNN_ERR_INVALID;
@@ -467,8 +487,16 @@ extern "C" int mscnn_roi_align_forward(const void* x_hi, const void* x_lo, int N
   roi_align_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)x_hi, (const __nv_bfloat16*)x_lo, rois, R, N, H, W, C, pooled_h, pooled_w,
       spatial_scale, pad_ratio, (__nv_bfloat16*)y_hi, (__nv_bfloat16*)y_lo, out_channels_total,
-      out_channel_offset);
+      out_channel_offset, dyn_R);
   return launch_check("roi_align");
+}
+
+extern "C" int mscnn_roi_align_forward(const void* x_hi, const void* x_lo, int N, int H, int W, int C,
+                                       const float* rois, int R, int pooled_h, int pooled_w,
+                                       float spatial_scale, float pad_ratio, void* y_hi, void* y_lo,
+                                       int out_channels_total, int out_channel_offset, void* stream) {
+  return mscnn_roi_align_forward_dyn(x_hi, x_lo, N, H, W, C, rois, R, pooled_h, pooled_w, spatial_scale, pad_ratio,
+                                     y_hi, y_lo, out_channels_total, out_channel_offset, nullptr, stream);
 }
 
 extern "C" int mscnn_deconv2x_forward(const void* x_hi, const void* x_lo, const float* w, void* y_hi,

@@ -53,6 +53,9 @@ def _declare(L):
     L.mscnn_net_layer_times.argtypes = [C.c_void_p, C.c_void_p]
     L.mscnn_net_num_proposals.argtypes = [C.c_void_p, C.c_int]
     L.mscnn_net_detect.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_void_p, C.c_void_p]
+    L.mscnn_net_set_graph.argtypes = [C.c_void_p, C.c_int]
+    L.mscnn_net_graph_replayed.argtypes = [C.c_void_p]
+    L.mscnn_net_resolve_rows.argtypes = [C.c_void_p]
     L.mscnn_net_detect_gather.restype = C.c_int
     L.mscnn_net_detect_gather.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_void_p, C.c_void_p]
     L.mscnn_net_detect_cascade.restype = C.c_int
@@ -233,6 +236,13 @@ class Net:
 
     def detect(self, cfg: capi.DetectCfg, dets_dev_ptr: int, counts_dev_ptr: int) -> None:
         capi.check(self._L.mscnn_net_detect(self._h, cfg, dets_dev_ptr, counts_dev_ptr), "net_detect")
+
+    def set_graph(self, on: bool = True) -> None:
+        """Replay whole forwards as one CUDA graph launch (after one eager forward; needs a non-default stream)."""
+        capi.check(self._L.mscnn_net_set_graph(self._h, int(on)), "net_set_graph")
+
+    def graph_replayed(self) -> bool:
+        return bool(self._L.mscnn_net_graph_replayed(self._h))
 
     def detect_gather(self, cfg: capi.DetectCfg, comm, payload_all_ptr: int) -> None:
         """Final detections of this rank packed into its slot of `payload_all` + ONE all-gather on the communicator's

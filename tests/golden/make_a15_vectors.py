@@ -1,0 +1,111 @@
+"""Hand-derived known answers for the MATLAB post-process: the reference has no test, fixture or
+executable for it here (no MATLAB / Octave), so the restatement (oracle/port.detect_postprocess, oracle_bbnms_maxg) and
+the device kernels are pinned to answers worked out BY HAND from the reference's own source lines
+(/root/reference/examples/kitti_car/run_mscnn_detection.m:75-120, /root/reference/utils/bbNms.m:75-126).  This file
+writes tests/golden/a15_postprocess_cases.json; every case carries its derivation.  It imports nothing from the repo:
+the expected numbers are literals.
+
+    python tests/golden/make_a15_vectors.py
+
+It stays PARITY-UNPINNED AGAINST MATLAB ITSELF; what these vectors pin is that three independent
+readings of the same source lines agree: the hand derivations below, the numpy/C restatement, and the CUDA kernels.
+"""
+import json
+import math
+from pathlib import Path
+
+cases = []
+
+# ---------------------------------------------------------------------------------------------- bbNms 'maxg'
+cases.append(dict(
+    name="overlap_exactly_half_is_kept",
+    kind="bbnms", overlap=0.5,
+    bbs=[[0, 0, 10, 10, 0.9], [0, 0, 10, 5, 0.8], [0, 0, 10, 6, 0.7]],
+    keep=[0, 1],
+    derivation="bbNms.m:118-122: o = iw*ih / (as(i)+as(j)-iw*ih); suppressed iff o > overlap (strict).  a vs b: "
+               "iw = 10, ih = 5, o = 50 / (100 + 50 - 50) = 0.5 exactly -> NOT suppressed.  a vs c: 60 / (100 + 60 - 60) "
+               "= 0.6 > 0.5 -> c suppressed.  Output in descending score order: a, b."))
+cases.append(dict(
+    name="greedy_skips_suppressed_suppressors",
+    kind="bbnms", overlap=0.5,
+    bbs=[[0, 0, 10, 10, 0.9], [2, 0, 10, 10, 0.8], [5, 0, 10, 10, 0.7]],
+    keep=[0, 2],
+    derivation="'maxg' = nmsMax(..., greedy = 1) (bbNms.m:107): the outer loop skips i when kp(i) == 0 (:114).  a vs b: "
+               "iw = 8, o = 80 / (200 - 80) = 0.667 > 0.5 -> b suppressed.  a vs c: iw = 5, o = 50 / 150 = 0.333 -> kept.  "
+               "b vs c would be 70 / 130 = 0.538 > 0.5, but b is suppressed and, being greedy, suppresses nobody -> c "
+               "survives.  (type 'max' would drop c.)"))
+cases.append(dict(
+    name="score_ties_keep_input_order",
+    kind="bbnms", overlap=0.5,
+    bbs=[[1, 0, 10, 10, 0.5], [0, 0, 10, 10, 0.5], [30, 30, 4, 4, 0.5]],
+    keep=[0, 2],
+    derivation="bbNms.m:111 sort(bbs(:,5),'descend'): MATLAB's sort is stable, equal scores keep their input order, so "
+               "row 1 is visited before row 2.  Rows 1 and 2: iw = 9, o = 90 / (200 - 90) = 0.818 > 0.5 -> row 2 "
+               "suppressed by row 1.  Row 3 is disjoint (iw <= 0 -> continue, :116).  Kept: rows 1, 3 in that order."))
+cases.append(dict(
+    name="touching_and_negative_width_boxes_never_overlap",
+    kind="bbnms", overlap=0.5,
+    bbs=[[0, 0, 10, 10, 0.9], [10, 0, 10, 10, 0.8], [50, 0, -5, 10, 0.7], [48, 0, 4, 10, 0.6]],
+    keep=[0, 1, 2, 3],
+    derivation="bbNms.m:116-117: iw = min(xe) - max(xs); iw <= 0 -> continue.  a / b share only the edge x = 10: iw = 0.  "
+               "Row 3 has a NEGATIVE width (what run_mscnn_detection.m:115 tw = min(tw, orgW - tx) yields for a box whose "
+               "left edge lies beyond the image): xe = 45 < xs = 50, so against row 4 (xs = 48, xe = 52) "
+               "iw = min(45, 52) - max(50, 48) = -5 <= 0 -> no suppression either way.  All four rows are kept."))
+cases.append(dict(
+    name="threshold_just_above_half",
+    kind="bbnms", overlap=0.5,
+    bbs=[[0, 0, 8, 8, 0.9], [0, 0, 8, 4.0625, 0.8]],
+    keep=[0],
+    derivation="o = (8 * 4.0625) / 64 = 32.5 / 64 = 0.5078125 (exact in binary) > 0.5 -> suppressed.  Guards the strict "
+               "comparison from the other side of case 1."))
+
+# -------------------------------------------------------------------------------- full post-process of one image
+ln3 = math.log(3.0)
+v_dh = math.log(2.0) / 0.2
+cases.append(dict(
+    name="decode_softmax_clip",
+    kind="postprocess", cls_id=2, net_hw=[120, 200], ratios=[1.0, 1.0],
+    proposals_score=[[0, 10, 20, 50, 100, 1.5]],
+    cls_pred=[[0.0, ln3, 0.0, 0.0, 0.0]],
+    bbox_pred=[[9, 9, 9, 9, 0.5, -0.25, 0.0, v_dh] + [7] * 12],
+    dets=[[12.0, 0.0, 40.0, 120.0, 3.0 / 7.0]],
+    tol=2e-6,
+    derivation="run_mscnn_detection.m:77-78: proposal [x1 y1 x2 y2] = [10 20 50 100] -> [x y w h] = [10 20 40 80].  :98-99 "
+               "class-2 deltas columns 5..8 = [0.5 -0.25 0 ln(2)/0.2] .* [.1 .1 .2 .2] = [0.05 -0.025 0 ln 2].  :101-103 "
+               "exp(cls_pred) = [1 3 1 1 1] -> prob = 3/7.  :104-109 ctr = (30, 60); tx = 0.05*40 + 30 = 32, ty = -0.025*80 "
+               "+ 60 = 58, tw = 40*exp(0) = 40, th = 80*exp(ln 2) = 160; top-left = (32 - 20, 58 - 80) = (12, -22).  "
+               ":114-115 tx = max(0, 12) = 12, ty = max(0, -22) = 0, tw = min(40, 200 - 12) = 40, th = min(160, 120 - 0) = 120."))
+cases.append(dict(
+    name="filter_bad_proposals_then_nms",
+    kind="postprocess", cls_id=2, net_hw=[400, 400], ratios=[1.0, 1.0],
+    proposals_score=[[0, 0, 0, 100, 100, 2.0],      # A
+                     [0, 20, 0, 120, 100, 1.0],     # B: overlaps A 80/120 = 0.667
+                     [0, 50, 50, 50, 90, 5.0],      # zero width  -> dropped at :82
+                     [0, 60, 60, 90, 60, 5.0],      # zero height -> dropped at :82
+                     [0, 200, 200, 300, 300, -10.5],  # score < proposal_thr = -10 -> dropped at :82
+                     [0, 200, 200, 300, 300, -10.0]],  # score == -10 stays (>=)
+    cls_pred=[[0, 2, 0, 0, 0], [0, 1, 0, 0, 0], [0, 9, 0, 0, 0], [0, 9, 0, 0, 0], [0, 9, 0, 0, 0], [0, 0, 0, 0, 0]],
+    bbox_pred=[[0.0] * 20] * 6,
+    dets=[[0.0, 0.0, 100.0, 100.0, math.exp(2) / (math.exp(2) + 4)], [200.0, 200.0, 100.0, 100.0, 0.2]],
+    tol=2e-6,
+    derivation="run_mscnn_detection.m:82 keep_id = score >= proposal_thr (-10) & w ~= 0 & h ~= 0: rows 3, 4 (zero extent) "
+               "and 5 (-10.5) go, row 6 (-10, '>=') stays.  Zero deltas: boxes are the proposals in [x y w h].  "
+               "prob(A) = e^2 / (e^2 + 4) = 0.6488, prob(B) = e / (e + 4) = 0.4046, prob(row 6) = 1/5.  bbNms 'maxg' 0.5: A vs B "
+               "iw = 80, o = 8000 / (20000 - 8000) = 0.667 -> B suppressed; row 6 is disjoint.  Output by descending "
+               "prob: A, row 6."))
+cases.append(dict(
+    name="ratios_rescale_to_the_original_image",
+    kind="postprocess", cls_id=2, net_hw=[768, 2560], ratios=[2.0, 4.0], org_hw=[384, 640],
+    proposals_score=[[0, 400, 100, 800, 300, 0.0]],
+    cls_pred=[[0.0, 0.0, 0.0, 0.0, 0.0]],
+    bbox_pred=[[0.0] * 20],
+    dets=[[100.0, 50.0, 100.0, 100.0, 0.2]],
+    tol=2e-6,
+    derivation="ratios = [imgH imgW] ./ [orgH orgW] = [768 2560] ./ [384 640] = [2 4] (:62-63).  Box [400 100 400 200] in "
+               "net pixels; :110-111 tx, tw divided by ratios(2) = 4 -> 100, 100; ty, th by ratios(1) = 2 -> 50, 100.  "
+               "Clip against orgW = 640, orgH = 384: unchanged.  prob = 1/5."))
+
+out = Path(__file__).resolve().parent / "a15_postprocess_cases.json"
+out.write_text(json.dumps(dict(source="hand-derived from run_mscnn_detection.m:75-120 and bbNms.m:75-126; see make_a15_vectors.py",
+                               cases=cases), indent=1))
+print(f"{len(cases)} cases -> {out}")

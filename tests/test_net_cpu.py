@@ -226,8 +226,77 @@ def _caffemodel(layers: dict, legacy=False) -> bytes:
     return out
 
 
-@pytest.mark.parametrize("legacy", [False, True])
-def test_caffemodel_wire_reader(tmp_path, legacy):
+def _caffe_pb():
+    """NetParameter / LayerParameter / V1LayerParameter / BlobProto / BlobShape message classes built with the
+    google.protobuf RUNTIME from a descriptor written out by hand from the reference's schema (no protoc in the image):
+    /root/reference/src/caffe/proto/caffe.proto:5-24 (BlobShape, BlobProto), :64-100 (NetParameter: name = 1,
+    layers = 2, layer = 100), :310-330 (LayerParameter: name = 1, type = 2, bottom = 3, top = 4, blobs = 7),
+    V1LayerParameter (bottom = 2, top = 3, name = 4, type = 5 (enum), blobs = 6).  An encoder independent of the
+    library's own reader and of the hand encoder above."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+    F = descriptor_pb2.FieldDescriptorProto
+    fd = descriptor_pb2.FileDescriptorProto(name="caffe_subset.proto", package="caffe_subset", syntax="proto2")
+
+    def msg(name, fields):
+        m = fd.message_type.add(name=name)
+        for fname, num, ftype, label, extra in fields:
+            f = m.field.add(name=fname, number=num, type=ftype, label=label)
+            if extra.get("packed"):
+                f.options.packed = True
+            if "type_name" in extra:
+                f.type_name = ".caffe_subset." + extra["type_name"]
+    O, R = F.LABEL_OPTIONAL, F.LABEL_REPEATED
+    msg("BlobShape", [("dim", 1, F.TYPE_INT64, R, {"packed": True})])
+    msg("BlobProto", [("shape", 7, F.TYPE_MESSAGE, O, {"type_name": "BlobShape"}),
+                      ("data", 5, F.TYPE_FLOAT, R, {"packed": True}), ("diff", 6, F.TYPE_FLOAT, R, {"packed": True}),
+                      ("double_data", 8, F.TYPE_DOUBLE, R, {"packed": True}),
+                      ("num", 1, F.TYPE_INT32, O, {}), ("channels", 2, F.TYPE_INT32, O, {}),
+                      ("height", 3, F.TYPE_INT32, O, {}), ("width", 4, F.TYPE_INT32, O, {})])
+    msg("LayerParameter", [("name", 1, F.TYPE_STRING, O, {}), ("type", 2, F.TYPE_STRING, O, {}),
+                           ("bottom", 3, F.TYPE_STRING, R, {}), ("top", 4, F.TYPE_STRING, R, {}),
+                           ("blobs", 7, F.TYPE_MESSAGE, R, {"type_name": "BlobProto"})])
+    msg("V1LayerParameter", [("bottom", 2, F.TYPE_STRING, R, {}), ("top", 3, F.TYPE_STRING, R, {}),
+                             ("name", 4, F.TYPE_STRING, O, {}), ("type", 5, F.TYPE_INT32, O, {}),
+                             ("blobs", 6, F.TYPE_MESSAGE, R, {"type_name": "BlobProto"})])
+    msg("NetParameter", [("name", 1, F.TYPE_STRING, O, {}),
+                         ("layers", 2, F.TYPE_MESSAGE, R, {"type_name": "V1LayerParameter"}),
+                         ("layer", 100, F.TYPE_MESSAGE, R, {"type_name": "LayerParameter"})])
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = lambda n: message_factory.GetMessageClass(pool.FindMessageTypeByName("caffe_subset." + n))
+    return get("NetParameter")
+
+
+def _caffemodel_pb(layers: dict, mode: str) -> bytes:
+    """mode: "shape" (BlobShape), "legacy" (num/channels/height/width, blob.cpp:448-462), "double" (double_data),
+    "v1" (NetParameter.layers = V1LayerParameter, legacy dims)."""
+    net = _caffe_pb()(name="net")
+    for name, blobs in layers.items():
+        lp = net.layers.add(name=name, type=4) if mode == "v1" else net.layer.add(name=name, type="Convolution")
+        if mode != "v1":
+            lp.bottom.append("x")
+            lp.top.append(name)
+        for b in blobs:
+            bp = lp.blobs.add()
+            if mode in ("legacy", "v1"):
+                dims = [1] * (4 - b.ndim) + list(b.shape)     # legacy blobs index FROM THE END (blob.cpp:396-405)
+                bp.num, bp.channels, bp.height, bp.width = dims
+            else:
+                bp.shape.dim.extend(b.shape)
+            if mode == "double":
+                bp.double_data.extend(b.astype(np.float64).reshape(-1).tolist())
+            else:
+                bp.data.extend(b.reshape(-1).tolist())
+    return net.SerializeToString()
+
+
+@pytest.mark.parametrize("encoder,mode", [("hand", "shape"), ("hand", "legacy"), ("pb", "shape"), ("pb", "legacy"),
+                                          ("pb", "double"), ("pb", "v1")])
+def test_caffemodel_wire_reader(tmp_path, encoder, mode):
+    """Net::CopyTrainedLayersFrom(file) (net.cpp:787-803) through the library's own wire-format reader, against two
+    independent encoders: the hand encoder above and the google.protobuf runtime; BlobShape and legacy 4-D dimensions
+    (conv bias 1x1x1xN, InnerProduct weight 1x1xMxN: matched from the end of the shape, blob.cpp:392-413), double_data,
+    and a V1 file (NetParameter.layers), which the reference upgrades on load."""
     from mscnn_b200.net import Net
     text = ('input: "data" input_dim: 1 input_dim: 64 input_dim: 6 input_dim: 6\n'
             'layer { bottom: "data" top: "c" name: "c" type: "Convolution" convolution_param { num_output: 8 kernel_size: 3 } }\n'
@@ -236,21 +305,40 @@ def test_caffemodel_wire_reader(tmp_path, legacy):
     w = {"c": [rng.standard_normal((8, 64, 3, 3)).astype(np.float32), rng.standard_normal(8).astype(np.float32)],
          "f": [rng.standard_normal((5, 128)).astype(np.float32), rng.standard_normal(5).astype(np.float32)],
          "not_in_net": [np.zeros((2, 2), np.float32)]}          # ignored like net.cpp:760-763
-    if legacy:
-        w["c"][1] = w["c"][1].reshape(1, 1, 1, 8)
-        w["f"][0] = w["f"][0].reshape(1, 1, 5, 128)
-        w["f"][1] = w["f"][1].reshape(1, 1, 1, 5)
     path = tmp_path / "m.caffemodel"
-    path.write_bytes(_caffemodel(w, legacy))
+    if encoder == "hand":
+        legacy = mode == "legacy"
+        wl = {k: [b.reshape((1,) * (4 - b.ndim) + b.shape) for b in v] for k, v in w.items()} if legacy else w
+        path.write_bytes(_caffemodel(wl, legacy))
+    else:
+        path.write_bytes(_caffemodel_pb(w, mode))
     net = Net(text)
-    if legacy:
-        pytest.skip("legacy 4-D shapes only match 4-D params (blob.cpp:392-413); covered for conv weights below")
     net.copy_from(str(path))
-    import ctypes as C
-    from mscnn_b200 import capi
-    # read the params back through the blob-of-params path: set_param round trip is exact, so compare
-    # via a second net that receives the same arrays through set_params
     ref = Net(text)
     ref.set_params({k: v for k, v in w.items() if k != "not_in_net"})
     assert net.layer_param_strings() == ref.layer_param_strings()
     assert net.param_checksums() == ref.param_checksums()
+    for name in ("c", "f"):
+        for i, b in enumerate(w[name]):
+            assert np.array_equal(net.param(name, i).reshape(-1), b.reshape(-1)), (name, i)
+
+
+def test_caffemodel_truncated_file_is_rejected(tmp_path):
+    """A file cut in the middle of a blob must abort like Caffe's ReadProtoFromBinaryFileOrDie (upgrade_proto.cpp),
+    not read past the buffer; a file whose layers match nothing loads nothing and says so."""
+    import subprocess
+    import sys
+    text = ('input: "data" input_dim: 1 input_dim: 64 input_dim: 6 input_dim: 6\n'
+            'layer { bottom: "data" top: "c" name: "c" type: "Convolution" convolution_param { num_output: 8 kernel_size: 3 } }\n')
+    w = {"c": [np.ones((8, 64, 3, 3), np.float32), np.ones(8, np.float32)]}
+    full = _caffemodel_pb(w, "shape")
+    bad = tmp_path / "cut.caffemodel"
+    bad.write_bytes(full[: len(full) // 2])
+    code = "import sys; from mscnn_b200.net import Net; n = Net(sys.argv[1]); n.copy_from(sys.argv[2])"
+    root = str(Path(__file__).resolve().parents[1])
+    r = subprocess.run([sys.executable, "-c", code, text, str(bad)], capture_output=True, text=True, cwd=root)
+    assert r.returncode != 0 and "malformed caffemodel" in r.stderr
+    other = tmp_path / "other.caffemodel"
+    other.write_bytes(_caffemodel_pb({"zzz": [np.ones((2, 2), np.float32)]}, "shape"))
+    r = subprocess.run([sys.executable, "-c", code, text, str(other)], capture_output=True, text=True, cwd=root)
+    assert r.returncode == 0 and "none of its 1 layers matches" in r.stderr

@@ -47,12 +47,29 @@ def run(name, proto, H, W, B, cfg, steps, warmup):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
+        launches = (capi.lib().mscnn_kernel_launch_count() - n0) // steps
+        # the same loop with whole forwards replayed as ONE CUDA graph launch (Net.set_graph; the first forward after
+        # switching it on runs eagerly, the second is captured, later ones are replays)
+        net.set_graph(True)
+        for _ in range(max(warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        replayed = net.graph_replayed()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_graph = e0.elapsed_time(e1) / steps
+        net.set_graph(False)
         lt = net.time_layers()
         out["fp32_faithful" if mode == "fp32" else "bf16"] = {
             "ms_per_step": ms, "value": B / (ms / 1e3), "unit": "images/s",
+            "graph": {"ms_per_step": ms_graph, "value": B / (ms_graph / 1e3), "replayed": bool(replayed)},
             "proposals_per_image": net.num_proposals() / B, "detections_per_image": float(cnt.float().mean().item()),
-            "kernel_launches_per_step": (capi.lib().mscnn_kernel_launch_count() - n0) // steps,
-            "top_layers_ms": sorted(((round(v, 3), k) for k, v in lt.items()), reverse=True)[:6]}
+            "kernel_launches_per_step": launches,
+            "layers_ms_sum": round(sum(lt.values()), 3),
+            "top_layers_ms": sorted(((round(v, 3), k) for k, v in lt.items()), reverse=True)[:12]}
         del net
     mnet.set_precision("fp32")
     return out
@@ -67,7 +84,9 @@ def main():
     from mscnn_b200 import capi, models, net as mnet
     torch.cuda.set_device(0)
     mnet.set_device(0)
-    mnet.set_stream(torch.cuda.current_stream().cuda_stream)
+    side = torch.cuda.Stream()          # a CUDA graph cannot be captured on the legacy default stream
+    torch.cuda.set_stream(side)
+    mnet.set_stream(side.cuda_stream)
     res = {"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "data": "synthetic (mscnn_b200/synth.py, seed 1706)"}
     cfg = mnet.kitti_detect_cfg(576, 1920)
     res["config1"] = run("mscnn-7s-576-2x full detection forward, 1x3x576x1920 (BASELINE.json configs[1])",
