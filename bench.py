@@ -90,8 +90,9 @@ class ClockSampler:
         sm.sort()
         # median of the upper half = clocks while the GPU is loaded
         load = sm[len(sm) // 2:] if sm else []
+        pw = sorted(float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit())
         return {"sm_mhz": (load[len(load) // 2] if load else None), "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "power_w_max": (pw[-1] if pw else None), "reasons": sorted(reasons)}
 
 
 def conv_flops(net, n_images: int) -> tuple[float, int]:
@@ -284,6 +285,11 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=BATCH, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-bf16", action="store_true", help="skip the plain-bf16 measurement")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: 'peer' = the post-process kernel pushes its payload into every rank's buffer over NVLink "
+                         "(no collective kernel; default); 'nccl' = one ncclAllGather per step on a side stream (baseline)")
+    ap.add_argument("--generations", type=int, default=16,
+                    help="peer exchange: how many steps the ranks may drift apart (2 = meet every step)")
     ap.add_argument("--no-gather", action="store_true",
                     help="control run for the scaling analysis: N > 1 without the all-gather of the final detections")
     ap.add_argument("--resident-only", action="store_true", help="only the device-resident measurement (no e2e loops)")
@@ -335,21 +341,27 @@ def main() -> None:
     # (per-image counts in the payload header) + ONE ncclAllGather on the communicator's own stream, overlapping the
     # next step's trunk (mscnn_net_detect_gather).  torch.distributed only carries the NCCL id and the barriers.
     use_gather = world > 1 and not args.no_gather
-    comm = parallel.Comm() if use_gather else None
+    use_peer = use_gather and args.exchange == "peer"
+    comm = parallel.Comm() if (use_gather and not use_peer) else None
     per = parallel.payload_floats(B, cap)
-    payload_all = torch.zeros(per * world, device=dev) if use_gather else None
+    xchg = parallel.PeerExchange(B, cap, generations=args.generations) if use_peer else None
+    payload_all = torch.zeros(per * world, device=dev) if (use_gather and not use_peer) else None
     host_payload = torch.zeros(per).pin_memory() if use_gather else None
     cur_stream = torch.cuda.current_stream().cuda_stream
 
     def detect():
-        if use_gather:
+        if use_peer:
+            net.detect_push(cfg, xchg)          # post-process + push to every rank + flags: ONE set of kernels
+        elif use_gather:
             net.detect_gather(cfg, comm, payload_all.data_ptr())
         else:
             net.detect(cfg, dets.data_ptr(), cnt.data_ptr())
 
     def download():
         # device -> host read of this rank's result (its own packed detections when the exchange is on)
-        if use_gather:
+        if use_peer:
+            host_payload.copy_(xchg.gathered()[rank * per:(rank + 1) * per], non_blocking=True)
+        elif use_gather:
             host_payload.copy_(payload_all[rank * per:(rank + 1) * per], non_blocking=True)
         else:
             host_dets.copy_(dets, non_blocking=True)
@@ -408,7 +420,9 @@ def main() -> None:
         for i in range(steps):
             fn()
             ev[i + 1].record()
-        if use_gather:
+        if use_peer:
+            xchg.wait(cur_stream)               # the timed region ends when every rank's last payload has landed here
+        elif use_gather:
             comm.stream_wait(cur_stream)        # the timed region ends when the last step's all-gather has landed
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
@@ -433,7 +447,7 @@ def main() -> None:
         torch.cuda.synchronize()
         return
     results = {}
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local)      # every rank samples ITS GPU: the scaling analysis needs the slowest one's clocks
     for mode in (["fp32"] if args.no_bf16 else ["fp32", "bf16"]):
         mnet.set_precision(mode)
         if mode == "fp32" and sampler:
@@ -447,6 +461,12 @@ def main() -> None:
             # where the time goes at N > 1: each rank's own step times (device events between steps on ITS stream)
             mine = {"rank": rank, "min": round(step_ms[0], 3), "median": round(step_ms[len(step_ms) // 2], 3),
                     "max": round(step_ms[-1], 3), "sum": round(sum(step_ms), 3)}
+            mine["sm_mhz"] = clocks["sm_mhz"] if clocks else None
+            mine["power_w_max"] = clocks.get("power_w_max") if clocks else None
+            mine["reasons"] = clocks["reasons"] if clocks else None
+            if use_gather and not use_peer:
+                gt = sorted(comm.gather_times_ms(min(args.steps, 64)))
+                mine["gather_ms"] = {"min": round(gt[0], 4), "median": round(gt[len(gt) // 2], 4), "max": round(gt[-1], 4)}
             per_rank = [None] * world
             dist.all_gather_object(per_rank, mine)
         props = torch.tensor([float(net.num_proposals())], device=dev)
@@ -478,6 +498,11 @@ def main() -> None:
     if comm is not None:
         comm.synchronize()
         comm.close()
+    if xchg is not None:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()                      # nobody unmaps a buffer a peer may still be writing
+        xchg.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -534,9 +559,11 @@ def main() -> None:
         "dtype": "bf16x3 (fp32-faithful: 3-term bf16 split on tcgen05, fp32 accumulate in TMEM)",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B,
-                   "parallelism": (f"dp{world} image-parallel" + (", one ncclAllGather of the packed final detections per "
-                                   "step inside libmscnn_b200.so (side stream, overlaps the next step)" if use_gather
-                                   else (", exchange OFF (--no-gather control run)" if world > 1 else ""))),
+                   "parallelism": (f"dp{world} image-parallel" + (
+                       ", final detections pushed into every rank's buffer over NVLink by the post-process kernel itself "
+                       "(peer-mapped stores + flags, no collective kernel)" if use_peer else
+                       ", one ncclAllGather of the packed final detections per step inside libmscnn_b200.so (side stream)"
+                       if use_gather else (", exchange OFF (--no-gather control run)" if world > 1 else ""))),
                    "l2": "inputs larger than L2 (189 MB image batch + >10 GB of activations per step vs 126 MB L2)",
                    "weights": "seeded synthetic (mscnn_b200/synth.py), seed 1706"},
         "proposals_per_sec": r["props"] * args.steps / (r["ms"] / 1e3),

@@ -6,7 +6,7 @@
 //
 //   g++ -std=c++17 -O2 -I include -I /usr/local/cuda/include examples/multi_gpu_driver.cpp \
 //       -L mscnn_b200 -lmscnn_b200 -L /usr/local/cuda/lib64 -lcudart -lpthread -Wl,-rpath,$PWD/mscnn_b200 -o multi_gpu_driver
-//   ./multi_gpu_driver deploy.prototxt --gpus 8 --steps 20 --warmup 5 [--no-gather] [--verify]
+//   ./multi_gpu_driver deploy.prototxt --gpus 8 --steps 20 --warmup 5 [--exchange peer|nccl] [--no-gather] [--verify]
 //
 // Prints one line per rank (min / median / max step time on the device) and the whole-job images/s
 // (max over ranks of the timed region).  --verify: every rank checks that the gathered buffer holds, for every
@@ -72,17 +72,18 @@ struct RankResult {
 
 int main(int argc, char** argv) {
   if (argc < 2) {
-    std::fprintf(stderr, "usage: %s deploy.prototxt [--gpus N] [--steps K] [--warmup W] [--no-gather] [--verify]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s deploy.prototxt [--gpus N] [--steps K] [--warmup W] [--exchange peer|nccl] [--no-gather] [--verify]\n", argv[0]);
     return 2;
   }
   const std::string proto = argv[1];
   int gpus = 1, steps = 10, warmup = 3;
-  bool gather = true, verify = false;
+  bool gather = true, verify = false, peer = true;
   for (int i = 2; i < argc; ++i) {
     if (!std::strcmp(argv[i], "--gpus") && i + 1 < argc) gpus = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--steps") && i + 1 < argc) steps = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--warmup") && i + 1 < argc) warmup = std::atoi(argv[++i]);
     else if (!std::strcmp(argv[i], "--no-gather")) gather = false;
+    else if (!std::strcmp(argv[i], "--exchange") && i + 1 < argc) peer = std::strcmp(argv[++i], "nccl") != 0;
     else if (!std::strcmp(argv[i], "--verify")) verify = true;
   }
   int ndev = 0;
@@ -91,9 +92,13 @@ int main(int argc, char** argv) {
     std::fprintf(stderr, "%d GPUs requested, %d visible\n", gpus, ndev);
     return 2;
   }
-  std::vector<void*> comms(gpus, nullptr);
-  CK(mscnn_comm_init_all(comms.data(), gpus, nullptr));
-  std::printf("nccl %d, %d rank(s) in one process\n", mscnn_comm_nccl_version(), gpus);
+  std::vector<void*> comms(gpus, nullptr), xchgs(gpus, nullptr);
+  if (gather && !peer) {
+    CK(mscnn_comm_init_all(comms.data(), gpus, nullptr));
+    std::printf("nccl %d, %d rank(s) in one process\n", mscnn_comm_nccl_version(), gpus);
+  } else if (gather) {
+    std::printf("peer-memory exchange, %d rank(s) in one process\n", gpus);
+  }
 
   Barrier bar(gpus);
   std::vector<RankResult> res(gpus);
@@ -148,6 +153,12 @@ int main(int argc, char** argv) {
       per = mscnn_detect_payload_floats(batch, cfg.max_rois_per_image);
     }
     bar.wait();
+    if (gather && peer) {
+      CK(mscnn_xchg_create(&xchgs[rank], gpus, rank, per, 16));
+      bar.wait();
+      if (rank == 0) CK(mscnn_xchg_connect_local(xchgs.data(), gpus));
+      bar.wait();
+    }
     cudaMalloc(&payload_dev[rank], per * gpus * sizeof(float));
     cudaMemset(payload_dev[rank], 0, per * gpus * sizeof(float));
     float* dets = nullptr;
@@ -158,12 +169,17 @@ int main(int argc, char** argv) {
     auto step = [&]() {
       CK(mscnn_net_set_blob(net, in_name, host_in, in_count));   // pinned host -> device on the net's stream
       CK(mscnn_net_forward(net, 0, -1));
-      if (gather) CK(mscnn_net_detect_gather(net, &cfg, comms[rank], payload_dev[rank]));
+      if (gather && peer) CK(mscnn_net_detect_push(net, &cfg, xchgs[rank]));
+      else if (gather) CK(mscnn_net_detect_gather(net, &cfg, comms[rank], payload_dev[rank]));
       else CK(mscnn_net_detect(net, &cfg, dets, cnt));
     };
+    auto settle = [&]() {   // everything this rank sent and everything it should receive has landed
+      if (gather && peer) CK(mscnn_xchg_wait(xchgs[rank], stream));
+      cudaStreamSynchronize(stream);
+      if (gather && !peer) CK(mscnn_comm_synchronize(comms[rank]));
+    };
     for (int s = 0; s < warmup; ++s) step();
-    cudaStreamSynchronize(stream);
-    if (gather) CK(mscnn_comm_synchronize(comms[rank]));
+    settle();
     bar.wait();
     std::vector<cudaEvent_t> ev(steps + 1);
     for (auto& e : ev) cudaEventCreate(&e);
@@ -172,8 +188,7 @@ int main(int argc, char** argv) {
       step();
       cudaEventRecord(ev[s + 1], stream);
     }
-    cudaStreamSynchronize(stream);
-    if (gather) CK(mscnn_comm_synchronize(comms[rank]));
+    settle();
     RankResult& r = res[rank];
     for (int s = 0; s < steps; ++s) {
       float ms = 0.f;
@@ -185,7 +200,8 @@ int main(int argc, char** argv) {
     if (gather && verify) {
       // this rank's own packed detections, computed once more without the exchange ...
       std::vector<float> all(per * gpus);
-      cudaMemcpy(all.data(), payload_dev[rank], all.size() * sizeof(float), cudaMemcpyDeviceToHost);
+      const float* gathered = peer ? mscnn_xchg_buffer(xchgs[rank]) : payload_dev[rank];
+      cudaMemcpy(all.data(), gathered, all.size() * sizeof(float), cudaMemcpyDeviceToHost);
       r.own_payload.assign(all.begin() + per * rank, all.begin() + per * (rank + 1));
       bar.wait();
       // ... must be what every other rank received in slot `rank` (header + rows; the tail behind the rows is unused)
@@ -196,6 +212,7 @@ int main(int argc, char** argv) {
       }
     }
     bar.wait();
+    if (xchgs[rank]) mscnn_xchg_destroy(xchgs[rank]);
     mscnn_net_destroy(net);
     cudaFree(dets);
     cudaFree(cnt);
@@ -220,5 +237,6 @@ int main(int argc, char** argv) {
   std::printf("images_per_s %.2f (batch %d x %d GPUs x %d steps / %.3f ms, max over ranks; gather %s)\n",
               1e3 * batch * gpus * steps / worst, batch, gpus, steps, worst, gather ? "on" : "off");
   for (void* c : comms) mscnn_comm_destroy(c);
+  std::printf("exchange: %s\n", !gather ? "off" : peer ? "peer-memory push (no collective kernel)" : "ncclAllGather");
   return ok ? 0 : 1;
 }

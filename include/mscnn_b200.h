@@ -481,7 +481,41 @@ MSCNN_API int mscnn_comm_info(void* comm, int* nranks, int* rank, int* device);
 MSCNN_API int mscnn_comm_all_gather(void* comm, float* buf_all, size_t floats_per_rank, void* producer_stream);
 MSCNN_API int mscnn_comm_stream_wait(void* comm, void* stream);
 MSCNN_API int mscnn_comm_synchronize(void* comm);
+/* device durations (ms) of the last <= 64 collectives on the communicator's stream, oldest first (each includes the
+ * wait for the slowest peer); returns the number written, waits for the last collective */
+MSCNN_API int mscnn_comm_gather_times(void* comm, float* host_ms, int cap);
 MSCNN_API int mscnn_net_detect_gather(void* net, const mscnn_detect_cfg* cfg, void* comm, float* payload_all);
+
+
+/* Peer-memory exchange: the same all-gather of the packed final detections WITHOUT a collective kernel.  The
+ * post-process kernel of rank r stores its payload directly into slot r of every rank's gather buffer through
+ * peer-mapped pointers over NVLink and then publishes the step's sequence number in every rank's flag word; receiving
+ * is cuStreamWaitValue32 on the local flags.  No launch, no SM held, no rendezvous (an ncclAllGather kernel spins on
+ * its SMs until the slowest peer joins, which stalls one persistent convolution CTA per occupied SM: 2.2 ms per step at
+ * 8 GPUs, profiles/r02_summary.md).  This is the default exchange of bench.py; mscnn_net_detect_gather stays as the
+ * NCCL baseline.
+ *   mscnn_xchg_create: one per rank on its device ([generations][nranks][floats_per_rank] + flags); generations
+ *   >= 2 = how many steps the ranks may drift apart (step s uses generation s mod G; a sender reuses a generation only
+ *   after every peer has pushed step s - G + 1).  Ranks that must meet every step pay E[max over ranks] of the per-step
+ *   jitter per step; with G = 16 they pay it once per 16 steps.
+ *   same process (one host thread per GPU): mscnn_xchg_connect_local(all objects);
+ *   other processes: mscnn_xchg_ipc_handle -> (host transport) -> mscnn_xchg_open_peer_ipc for every peer.
+ *   mscnn_net_detect_push / mscnn_detect_postprocess_push: post-process + push + flags, on the net's / given stream.
+ *   mscnn_xchg_wait(x, stream): the stream waits until all ranks' payloads of the last push are in mscnn_xchg_buffer(x)
+ *   ([nranks][floats_per_rank]); consume them on that stream before the next push. */
+#define MSCNN_XCHG_HANDLE_BYTES 64
+MSCNN_API int mscnn_xchg_create(void** xchg, int nranks, int rank, size_t floats_per_rank, int generations);
+MSCNN_API int mscnn_xchg_destroy(void* xchg);
+MSCNN_API int mscnn_xchg_ipc_handle(void* xchg, void* host_handle64);
+MSCNN_API int mscnn_xchg_open_peer_ipc(void* xchg, int peer_rank, const void* host_handle64);
+MSCNN_API int mscnn_xchg_connect_local(void** xchgs, int n);
+MSCNN_API int mscnn_xchg_info(void* xchg, int* nranks, int* rank, size_t* floats_per_rank);
+MSCNN_API const float* mscnn_xchg_buffer(void* xchg);
+MSCNN_API int mscnn_xchg_wait(void* xchg, void* stream);
+MSCNN_API int mscnn_detect_postprocess_push(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
+                                  const float* cls_pred, const float* bbox_pred, const int* num_rois, void* workspace,
+                                  size_t workspace_bytes, void* xchg, void* stream);
+MSCNN_API int mscnn_net_detect_push(void* net, const mscnn_detect_cfg* cfg, void* xchg);
 
 #ifdef __cplusplus
 }

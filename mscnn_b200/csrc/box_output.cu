@@ -23,6 +23,7 @@
 
 #include "mscnn_b200.h"
 #include "launch_count.h"
+#include "xchg.h"
 
 namespace mscnn {
 
@@ -559,6 +560,73 @@ __global__ void detect_write_packed_kernel(const float4* __restrict__ sboxes, co
   }
 }
 
+// The same packing with the EXCHANGE FUSED IN (mscnn_net_detect_push): block n packs image n's rows into this rank's slot
+// of its OWN gather buffer, then copies exactly that row range into the same slot of every other rank's buffer through
+// peer-mapped pointers over NVLink with 16-byte coalesced stores (the unaligned ends with scalar ones); the last block to
+// finish copies the header and publishes the step's sequence number in each rank's flag word (release at system scope).
+// No collective kernel, no rendezvous: a rank never waits for a peer to send, and nothing but the receivers'
+// cuStreamWaitValue32 ever waits to receive.  (First version: one 4-byte remote store per float, 240k NVLink
+// transactions per step at 8 GPUs = 1.3 ms per step; an ncclAllGather instead: its kernel spins on SMs until the slowest
+// peer joins, 1.8 ms per step; profiles/r02_summary.md.)
+__global__ void detect_push_packed_kernel(const float4* __restrict__ sboxes, const float* __restrict__ sscores,
+                                          const int* __restrict__ keep_idx, const int* __restrict__ keep_count,
+                                          int Kpad, int cap, int N, mscnn::PushTargets t, unsigned int seq,
+                                          unsigned int* __restrict__ done_counter) {
+  const int n = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  int off = 0;
+  for (int m = 0; m < n; ++m) off += min(keep_count[m], cap);
+  const int cnt = min(keep_count[n], cap);
+  const int hdr = (2 + N + 3) & ~3;
+  float* lbase = t.data[t.self];
+  for (int r = tid; r < cnt; r += nt) {
+    const int src = keep_idx[(size_t)n * Kpad + r];
+    const float4 b = sboxes[(size_t)n * Kpad + src];
+    float* o = lbase + hdr + (size_t)(off + r) * 5;
+    o[0] = b.x; o[1] = b.y; o[2] = b.z; o[3] = b.w; o[4] = sscores[(size_t)n * Kpad + src];
+  }
+  if (tid == 0) {
+    int* head = reinterpret_cast<int*>(lbase);
+    head[2 + n] = cnt;
+    if (n == N - 1) {
+      head[0] = N;
+      head[1] = off + cnt;
+    }
+  }
+  __syncthreads();
+  // this block's rows = floats [f0, f1) of the slot; [a0, a1) is the 16-byte aligned middle (slot bases are aligned)
+  const size_t f0 = (size_t)hdr + (size_t)off * 5, f1 = f0 + (size_t)cnt * 5;
+  size_t a0 = (f0 + 3) & ~(size_t)3, a1 = f1 & ~(size_t)3;
+  if (a0 > a1) a0 = a1 = f1;
+  for (int d = 0; d < t.count; ++d) {
+    if (d == t.self) continue;
+    float* dbase = t.data[d];
+    const float4* src4 = reinterpret_cast<const float4*>(lbase + a0);
+    float4* dst4 = reinterpret_cast<float4*>(dbase + a0);
+    const size_t n4 = (a1 - a0) / 4;
+    for (size_t i = tid; i < n4; i += nt) dst4[i] = src4[i];
+    for (size_t i = f0 + tid; i < a0 && i < f1; i += nt) dbase[i] = lbase[i];
+    for (size_t i = (a1 > f0 ? a1 : f0) + tid; i < f1; i += nt) dbase[i] = lbase[i];
+  }
+  // publish: every block's stores are fenced at system scope; the last block to arrive copies the header (all blocks'
+  // counts are in the local slot by then) and writes the flags
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool last;
+  if (tid == 0) last = (atomicAdd(done_counter, 1u) == (unsigned)(N - 1));
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    for (int d = 0; d < t.count; ++d) {
+      if (d == t.self) continue;
+      for (int i = tid; i < hdr; i += nt) t.data[d][i] = __ldcg(lbase + i);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < t.count) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(t.flag[tid]), "r"(seq) : "memory");
+    if (tid == 0) *done_counter = 0u;  // re-armed for the next launch (stream-ordered)
+  }
+}
+
 static int next_pow2(int v) {
   int p = 64;
   while (p < v) p <<= 1;
@@ -735,12 +803,13 @@ extern "C" int mscnn_detect_workspace_bytes(const mscnn_detect_cfg* cfg, int N, 
 
 static int detect_run(bool cascade, const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
                       const float* cls_pred, const float* bbox_pred, const int* num_rois, void* workspace,
-                      size_t workspace_bytes, float* dets, int* det_counts, void* stream_v, float* payload = nullptr) {
+                      size_t workspace_bytes, float* dets, int* det_counts, void* stream_v, float* payload = nullptr,
+                      const mscnn::PushTargets* push = nullptr, unsigned int seq = 0, unsigned int* done_counter = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_v;
   int Kpad;
   const int rc = det_cfg_check(cfg, N, &Kpad);
   if (rc) return rc;
-  if (!proposals_score || !cls_pred || !bbox_pred || !num_rois || !workspace || (!payload && (!dets || !det_counts)))
+  if (!proposals_score || !cls_pred || !bbox_pred || !num_rois || !workspace || (!payload && !push && (!dets || !det_counts)))
     return MSCNN_ERR_INVALID;
   const DetWs w = plan_det_ws(N, Kpad);
   if (workspace_bytes < w.total) return MSCNN_ERR_NOMEM;
@@ -783,7 +852,10 @@ static int detect_run(bool cascade, const mscnn_detect_cfg* cfg, int N, const fl
   mscnn::note_launch();
   nms_scan_kernel<<<N, kScanThreads, scan_smem, stream>>>(mask, counts, Kpad, words, 0, keep_idx, keep_count);
   mscnn::note_launch();
-  if (payload)
+  if (push)
+    detect_push_packed_kernel<<<N, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, Kpad,
+                                                    cfg->max_rois_per_image, N, *push, seq, done_counter);
+  else if (payload)
     detect_write_packed_kernel<<<N, 256, 0, stream>>>(sboxes, sscores, keep_idx, keep_count, Kpad,
                                                      cfg->max_rois_per_image, N, payload);
   else
@@ -807,7 +879,8 @@ extern "C" int mscnn_detect_postprocess(const mscnn_detect_cfg* cfg, int N, cons
 
 extern "C" size_t mscnn_detect_payload_floats(int N, int max_rois_per_image) {
   if (N <= 0 || max_rois_per_image <= 0) return 0;
-  return (size_t)((2 + N + 3) & ~3) + (size_t)N * max_rois_per_image * 5;
+  // header and rows, rounded up to 16 bytes so that consecutive slots of a gather buffer stay 16-byte aligned
+  return ((size_t)((2 + N + 3) & ~3) + (size_t)N * max_rois_per_image * 5 + 3) & ~(size_t)3;
 }
 
 extern "C" int mscnn_detect_postprocess_packed(const mscnn_detect_cfg* cfg, int N, const float* proposals_score,
@@ -816,6 +889,15 @@ extern "C" int mscnn_detect_postprocess_packed(const mscnn_detect_cfg* cfg, int 
   if (!payload) return MSCNN_ERR_INVALID;
   return detect_run(false, cfg, N, proposals_score, cls_pred, bbox_pred, num_rois, workspace, workspace_bytes,
                     nullptr, nullptr, stream, payload);
+}
+
+// internal entry of the peer-memory exchange (xchg.cu): post-process + fused push
+int mscnn::detect_postprocess_push(const mscnn_detect_cfg* cfg, int N, const float* proposals_score, const float* cls_pred,
+                                   const float* bbox_pred, const int* num_rois, void* workspace, size_t workspace_bytes,
+                                   const PushTargets* push, unsigned int seq, unsigned int* done_counter, void* stream) {
+  if (!push || push->count < 1 || push->count > kMaxPushRanks || !done_counter) return MSCNN_ERR_INVALID;
+  return detect_run(false, cfg, N, proposals_score, cls_pred, bbox_pred, num_rois, workspace, workspace_bytes, nullptr,
+                    nullptr, stream, nullptr, push, seq, done_counter);
 }
 
 extern "C" int mscnn_cascade_detect_postprocess(const mscnn_detect_cfg* cfg, int N, const float* proposals,

@@ -411,6 +411,28 @@ int mscnn_net_detect_gather(void* hv, const mscnn_detect_cfg* cfg, void* comm, f
   if (rc) return rc;
   return mscnn_comm_all_gather(comm, payload_all, per, Caffe::stream());
 }
+// Final detections of this rank packed AND pushed into every rank's gather buffer by the post-process kernel itself
+// (peer-memory exchange, xchg.cu): no collective, nothing else to launch.
+int mscnn_net_detect_push(void* hv, const mscnn_detect_cfg* cfg, void* xchg) {
+  NetHandle* h = H(hv);
+  if (!h->box || !xchg || !h->net->has_blob("proposals_score") || !h->net->has_blob("cls_pred") ||
+      !h->net->has_blob("bbox_pred"))
+    return MSCNN_ERR_INVALID;
+  const int N = h->net->input_blobs()[0]->num();
+  if (cfg->max_rois_per_image < h->box->max_rows_per_image()) return MSCNN_ERR_INVALID;
+  size_t need = 0;
+  int rc = mscnn_detect_workspace_bytes(cfg, N, &need);
+  if (rc) return rc;
+  if (need > h->det_ws_bytes) {
+    if (h->det_ws) cudaFree(h->det_ws);
+    if (cudaMalloc(&h->det_ws, need) != cudaSuccess) return MSCNN_ERR_NOMEM;
+    h->det_ws_bytes = need;
+  }
+  return mscnn_detect_postprocess_push(cfg, N, h->net->blob_by_name("proposals_score")->gpu_data(),
+                                       h->net->blob_by_name("cls_pred")->gpu_data(),
+                                       h->net->blob_by_name("bbox_pred")->gpu_data(), h->box->num_out_device(), h->det_ws,
+                                       h->det_ws_bytes, xchg, Caffe::stream());
+}
 int mscnn_net_detect_cascade(void* hv, const mscnn_detect_cfg* cfg, const char* proposals_blob,
                              const char* cls_prob_blob, const char* output_bbox_blob, float* dets_dev,
                              int* det_counts_dev) {

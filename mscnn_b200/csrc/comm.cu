@@ -83,6 +83,11 @@ struct Comm {
   cudaEvent_t produced = nullptr;           // producer stream's tail -> collective
   cudaEvent_t done = nullptr;               // collective finished
   bool done_valid = false;
+  // device time of the last kTimed collectives (start / end on the communicator's stream): the collective's own
+  // duration INCLUDING its wait for the slowest peer -- what the scaling analysis needs (mscnn_comm_gather_times)
+  static constexpr int kTimed = 64;
+  cudaEvent_t t0[kTimed] = {}, t1[kTimed] = {};
+  unsigned long long issued = 0;
 };
 
 int nccl_fail(const char* what, ncclResult_t r) {
@@ -95,6 +100,8 @@ int finish_init(Comm* c) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return MSCNN_ERR_CUDA;
   if (cudaEventCreateWithFlags(&c->produced, cudaEventDisableTiming) != cudaSuccess) return MSCNN_ERR_CUDA;
   if (cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) != cudaSuccess) return MSCNN_ERR_CUDA;
+  for (int i = 0; i < Comm::kTimed; ++i)
+    if (cudaEventCreate(&c->t0[i]) != cudaSuccess || cudaEventCreate(&c->t1[i]) != cudaSuccess) return MSCNN_ERR_CUDA;
   return MSCNN_OK;
 }
 
@@ -172,6 +179,10 @@ int mscnn_comm_destroy(void* comm) {
   if (c->comm && api()) g_api.CommDestroy(c->comm);
   if (c->produced) cudaEventDestroy(c->produced);
   if (c->done) cudaEventDestroy(c->done);
+  for (int i = 0; i < Comm::kTimed; ++i) {
+    if (c->t0[i]) cudaEventDestroy(c->t0[i]);
+    if (c->t1[i]) cudaEventDestroy(c->t1[i]);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   cudaSetDevice(prev);
   delete c;
@@ -209,12 +220,31 @@ int mscnn_comm_all_gather(void* comm, float* buf_all, size_t floats_per_rank, vo
   if (!c || !a || !buf_all || floats_per_rank == 0) return MSCNN_ERR_INVALID;
   if (cudaEventRecord(c->produced, static_cast<cudaStream_t>(producer_stream)) != cudaSuccess) return MSCNN_ERR_CUDA;
   if (cudaStreamWaitEvent(c->stream, c->produced, 0) != cudaSuccess) return MSCNN_ERR_CUDA;
+  const int slot = static_cast<int>(c->issued % Comm::kTimed);
+  cudaEventRecord(c->t0[slot], c->stream);
   const ncclResult_t r = a->AllGather(buf_all + (size_t)c->rank * floats_per_rank, buf_all, floats_per_rank, ncclFloat32,
                                       c->comm, c->stream);
   if (r != ncclSuccess) return nccl_fail("ncclAllGather", r);
+  cudaEventRecord(c->t1[slot], c->stream);
+  ++c->issued;
   if (cudaEventRecord(c->done, c->stream) != cudaSuccess) return MSCNN_ERR_CUDA;
   c->done_valid = true;
   return MSCNN_OK;
+}
+
+// Device durations (ms) of the most recent collectives, oldest first; returns how many were written (<= cap, <= 64).
+// Waits for the last one.
+int mscnn_comm_gather_times(void* comm, float* host_ms, int cap) {
+  Comm* c = static_cast<Comm*>(comm);
+  if (!c || !host_ms || cap <= 0) return MSCNN_ERR_INVALID;
+  if (c->done_valid && cudaEventSynchronize(c->done) != cudaSuccess) return MSCNN_ERR_CUDA;
+  const unsigned long long have = c->issued < (unsigned long long)Comm::kTimed ? c->issued : Comm::kTimed;
+  const int n = static_cast<int>(have < (unsigned long long)cap ? have : cap);
+  for (int i = 0; i < n; ++i) {
+    const int slot = static_cast<int>((c->issued - n + i) % Comm::kTimed);
+    if (cudaEventElapsedTime(&host_ms[i], c->t0[slot], c->t1[slot]) != cudaSuccess) return MSCNN_ERR_CUDA;
+  }
+  return n;
 }
 
 }  // extern "C"

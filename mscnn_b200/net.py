@@ -249,6 +249,13 @@ class Net:
         stream (mscnn_net_detect_gather); `comm` is a parallel.Comm."""
         capi.check(self._L.mscnn_net_detect_gather(self._h, cfg, comm.handle, payload_all_ptr), "net_detect_gather")
 
+    def detect_push(self, cfg: capi.DetectCfg, xchg) -> None:
+        """Final detections packed and pushed into every rank's gather buffer by the post-process kernel itself
+        (mscnn_net_detect_push); `xchg` is a parallel.PeerExchange."""
+        from . import parallel
+        parallel._declare_xchg(self._L)
+        capi.check(self._L.mscnn_net_detect_push(self._h, cfg, xchg.handle), "net_detect_push")
+
     def detect_cascade(self, cfg: capi.DetectCfg, dets_dev_ptr: int, counts_dev_ptr: int, stage: str = "3rd",
                        cls_prob: str | None = None) -> None:
         """Final detections of a cascade net from one stage's blobs (run_cascademscnn.m:36-48):

@@ -31,8 +31,9 @@ def shard_range(rank: int, per_rank: int) -> tuple[int, int]:
 
 def payload_floats(batch: int, cap: int) -> int:
     """Floats per rank of the packed detection payload: int32 header [N, total, counts[N]] padded to a multiple of
-    4 words, then up to batch * cap rows of [x y w h prob] (mscnn_detect_payload_floats)."""
-    return ((2 + batch + 3) & ~3) + batch * cap * 5
+    4 words, then up to batch * cap rows of [x y w h prob]; the total rounded up to a multiple of 4
+    (mscnn_detect_payload_floats)."""
+    return (((2 + batch + 3) & ~3) + batch * cap * 5 + 3) & ~3
 
 
 def _declare(L):
@@ -47,6 +48,7 @@ def _declare(L):
     L.mscnn_comm_all_gather.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.mscnn_comm_stream_wait.argtypes = [C.c_void_p, C.c_void_p]
     L.mscnn_comm_synchronize.argtypes = [C.c_void_p]
+    L.mscnn_comm_gather_times.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
     L.mscnn_detect_payload_floats.restype = C.c_size_t
     L.mscnn_detect_payload_floats.argtypes = [C.c_int, C.c_int]
     L._comm_declared = True
@@ -86,6 +88,13 @@ class Comm:
     def synchronize(self) -> None:
         capi.check(self._L.mscnn_comm_synchronize(self._h), "comm_synchronize")
 
+    def gather_times_ms(self, last: int = 64) -> list[float]:
+        """Device durations of the most recent all-gathers on the communicator's stream (incl. the wait for peers)."""
+        buf = (C.c_float * last)()
+        n = self._L.mscnn_comm_gather_times(self._h, buf, last)
+        capi.check(min(n, 0), "comm_gather_times")
+        return [float(buf[i]) for i in range(n)]
+
     def close(self) -> None:
         if self._h:
             self._L.mscnn_comm_destroy(self._h)
@@ -96,6 +105,86 @@ class Comm:
             self.close()
         except Exception:
             pass
+
+
+XCHG_HANDLE_BYTES = 64
+
+
+def _declare_xchg(L):
+    if getattr(L, "_xchg_declared", False):
+        return
+    L.mscnn_xchg_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_size_t, C.c_int]
+    L.mscnn_xchg_destroy.argtypes = [C.c_void_p]
+    L.mscnn_xchg_ipc_handle.argtypes = [C.c_void_p, C.c_void_p]
+    L.mscnn_xchg_open_peer_ipc.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.mscnn_xchg_buffer.restype = C.c_void_p
+    L.mscnn_xchg_buffer.argtypes = [C.c_void_p]
+    L.mscnn_xchg_wait.argtypes = [C.c_void_p, C.c_void_p]
+    L.mscnn_net_detect_push.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_void_p]
+    L._xchg_declared = True
+
+
+class PeerExchange:
+    """One rank of the library's peer-memory exchange (mscnn_b200/csrc/xchg.cu): the post-process kernel stores this
+    rank's packed detections straight into every rank's gather buffer over NVLink and raises a flag; no collective.
+    The 64-byte CUDA IPC handles of the buffers travel through the initialised torch.distributed group (any backend)."""
+
+    def __init__(self, batch: int, cap: int, rank: int | None = None, world: int | None = None, generations: int = 16):
+        """generations: how many steps the ranks may drift apart (>= 2; see mscnn_xchg_create)."""
+        self._L = capi.lib()
+        _declare_xchg(self._L)
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        self.batch, self.cap = batch, cap
+        self.per = payload_floats(batch, cap)
+        h = C.c_void_p()
+        capi.check(self._L.mscnn_xchg_create(C.byref(h), self.world, self.rank, self.per, generations), "xchg_create")
+        self._h = h
+        if self.world > 1:
+            buf = C.create_string_buffer(XCHG_HANDLE_BYTES)
+            capi.check(self._L.mscnn_xchg_ipc_handle(self._h, buf), "xchg_ipc_handle")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(buf.raw))
+            for p, hb in enumerate(handles):
+                if p != self.rank:
+                    capi.check(self._L.mscnn_xchg_open_peer_ipc(self._h, p, C.create_string_buffer(hb, XCHG_HANDLE_BYTES)),
+                               f"xchg_open_peer_ipc({p})")
+            dist.barrier()          # every rank has mapped every buffer before anybody pushes
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    def wait(self, stream_ptr: int) -> None:
+        """The stream waits (device side, no kernel) for every rank's payload of the last push."""
+        capi.check(self._L.mscnn_xchg_wait(self._h, stream_ptr), "xchg_wait")
+
+    def gathered(self) -> torch.Tensor:
+        """[world * payload_floats] view of the last push's gather buffer (valid behind wait())."""
+        ptr = self._L.mscnn_xchg_buffer(self._h)
+        assert ptr, "nothing pushed yet"
+        n = self.world * self.per
+        return _cuda_view(ptr, n)
+
+    def close(self) -> None:
+        if self._h:
+            self._L.mscnn_xchg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _cuda_view(ptr: int, n_floats: int) -> torch.Tensor:
+    """A torch view of `n_floats` fp32 at device address `ptr` (current device), without copying."""
+    class _Holder:
+        pass
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device="cuda")
 
 
 def pack_payload(dets: np.ndarray, counts: np.ndarray, cap: int) -> np.ndarray:
