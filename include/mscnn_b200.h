@@ -444,6 +444,9 @@ MSCNN_API int mscnn_net_forward(void* net, int from_layer, int to_layer); /* inc
 MSCNN_API int mscnn_net_resolve_rows(void* net);
 MSCNN_API int mscnn_net_set_graph(void* net, int on);
 MSCNN_API int mscnn_net_graph_replayed(void* net);
+/* Fused groups: the layer that does layer i's work (a Pooling folded into its convolution's epilogue, a sibling
+ * ROIPooling pooled by the group's leader), i itself otherwise.  mscnn_net_forward(from, ...) widens `from` back to it. */
+MSCNN_API int mscnn_net_fused_producer(void* net, int layer);
 MSCNN_API int mscnn_net_set_layer_timing(void* net, int on);
 MSCNN_API int mscnn_net_layer_times(void* net, float* ms);                 /* ms per layer, last forward */
 MSCNN_API int mscnn_net_num_proposals(void* net, int image);               /* image < 0: whole batch */

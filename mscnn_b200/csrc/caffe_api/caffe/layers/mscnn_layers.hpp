@@ -130,6 +130,7 @@ class CAFFE_API PoolingLayer : public Layer<Dtype> {
   int stride() const { return stride_; }
   int mode() const { return mode_; }
   void mark_done_by_producer() { done_by_producer_ = true; }  // the convolution's epilogue pooled already
+  virtual void ResetFusedState() { done_by_producer_ = false; }
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
   int kernel_, stride_, mode_, pooled_h_, pooled_w_;
@@ -283,6 +284,7 @@ class CAFFE_API ROIPoolingLayer : public Layer<Dtype> {
   int pooled_w() const { return pooled_width_; }
   int concat_offset() const { return concat_offset_; }
   void mark_done_by_leader() { done_by_leader_ = true; }
+  virtual void ResetFusedState() { done_by_leader_ = false; }
  protected:
   virtual void Forward_gpu(const vector<Blob<Dtype>*>& bottom, const vector<Blob<Dtype>*>& top);
   int channels_, height_, width_, pooled_height_, pooled_width_;

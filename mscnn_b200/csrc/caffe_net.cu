@@ -158,6 +158,8 @@ void Net<Dtype>::Init(const NetParameter& in_param) {
   for (size_t i = 0; i < blob_names_.size(); ++i) blob_names_index_[blob_names_[i]] = (int)i;
   for (size_t i = 0; i < layer_names_.size(); ++i) layer_names_index_[layer_names_[i]] = (int)i;
   layer_ms_.assign(layers_.size(), 0.f);
+  fused_producer_.resize(layers_.size());
+  for (size_t i = 0; i < layers_.size(); ++i) fused_producer_[i] = (int)i;
   if (!std::getenv("MSCNN_NO_FUSION")) {
     FuseLayers();
     if (!std::getenv("MSCNN_NO_POOL_FUSION")) FusePooling();
@@ -307,7 +309,17 @@ void Net<Dtype>::FuseLayers() {
           sibs.push_back(sb);
         }
     // only the FIRST producer in execution order leads; it needs every sibling's inputs
-    if (!sibs.empty()) sibs[0].layer->set_siblings(sibs);
+    if (!sibs.empty()) {
+      sibs[0].layer->set_siblings(sibs);
+      int leader = -1;
+      for (int k = 0; k < L; ++k) {
+        for (size_t b = 0; b < sibs.size(); ++b)
+          if (layers_[k].get() == sibs[b].layer) {
+            if (leader < 0) leader = k;
+            else fused_producer_[k] = leader;
+          }
+      }
+    }
     cat->set_fused(true);
   }
   // (b') ROIPooling whose ROI list descends from a BoxOutput layer (through Split / DecodeBBox, which keep the row
@@ -375,7 +387,16 @@ void Net<Dtype>::FusePooling() {
     for (size_t o = 0; o < net_output_blob_indices_.size(); ++o)
       is_net_output = is_net_output || (net_output_blob_indices_[o] == blob_id);
     conv->set_fused_pool(pool, top_vecs_[i][0], readers > 0 || is_net_output);
+    fused_producer_[i] = conv_idx;
   }
+}
+
+template <typename Dtype>
+int Net<Dtype>::fused_group_end(int layer) const {
+  int last = layer;
+  for (int k = layer + 1; k < (int)fused_producer_.size(); ++k)
+    if (fused_producer_[k] == layer) last = k;
+  return last;
 }
 
 // ---- CUDA graph replay of the whole forward (set_graph_mode) ----------------------------------------------------
@@ -451,6 +472,8 @@ template <typename Dtype>
 Dtype Net<Dtype>::ForwardFromTo(int start, int end) {
   CHECK_GE(start, 0);
   CHECK_LT(end, (int)layers_.size());
+  start = fused_producer(start);  // a range never starts inside a fused group (net.hpp fused_producer)
+  for (size_t i = 0; i < layers_.size(); ++i) layers_[i]->ResetFusedState();
   if (GraphForward(start, end)) {
     if (!lazy_rows_) ResolveRows();
     return Dtype(0);

@@ -266,7 +266,8 @@ int mscnn_net_forward(void* h, int from, int to) {
   }
   // Every forward records the point after which the input blob may be overwritten by the next asynchronous upload:
   // right behind the last layer that reads it.
-  const int c = nh->pending_consumer;
+  int c = nh->pending_consumer;
+  if (c >= 0) c = net->fused_group_end(net->fused_producer(c));  // never split a fused group
   if (c >= from && c < to) {
     net->ForwardFromTo(from, c);
     if (cudaEventRecord(nh->inputs_consumed, Caffe::stream()) != cudaSuccess) return MSCNN_ERR_CUDA;
@@ -331,6 +332,11 @@ int mscnn_net_graph_replayed(void* h) { return H(h)->net->graph_replayed_last_fo
 int mscnn_net_resolve_rows(void* h) {
   H(h)->net->ResolveRows();
   return MSCNN_OK;
+}
+// the layer that does layer i's work (itself unless the fusion pass folded it away); Net::fused_producer
+int mscnn_net_fused_producer(void* h, int layer) {
+  if (layer < 0 || layer >= (int)H(h)->net->layers().size()) return MSCNN_ERR_INVALID;
+  return H(h)->net->fused_producer(layer);
 }
 int mscnn_net_set_layer_timing(void* h, int on) {
   H(h)->net->set_layer_timing(on != 0);

@@ -53,6 +53,7 @@ def _declare(L):
     L.mscnn_net_layer_times.argtypes = [C.c_void_p, C.c_void_p]
     L.mscnn_net_num_proposals.argtypes = [C.c_void_p, C.c_int]
     L.mscnn_net_detect.argtypes = [C.c_void_p, C.POINTER(capi.DetectCfg), C.c_void_p, C.c_void_p]
+    L.mscnn_net_fused_producer.argtypes = [C.c_void_p, C.c_int]
     L.mscnn_net_set_graph.argtypes = [C.c_void_p, C.c_int]
     L.mscnn_net_graph_replayed.argtypes = [C.c_void_p]
     L.mscnn_net_resolve_rows.argtypes = [C.c_void_p]
@@ -236,6 +237,11 @@ class Net:
 
     def detect(self, cfg: capi.DetectCfg, dets_dev_ptr: int, counts_dev_ptr: int) -> None:
         capi.check(self._L.mscnn_net_detect(self._h, cfg, dets_dev_ptr, counts_dev_ptr), "net_detect")
+
+    def fused_producer(self, layer: str) -> str:
+        """The layer that does `layer`'s work (itself unless the fusion pass folded it into another layer)."""
+        i = self._L.mscnn_net_fused_producer(self._h, self.layer_names.index(layer))
+        return self.layer_names[i]
 
     def set_graph(self, on: bool = True) -> None:
         """Replay whole forwards as one CUDA graph launch (after one eager forward; needs a non-default stream)."""

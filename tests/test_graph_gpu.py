@@ -97,3 +97,27 @@ def test_rows_are_deferred_and_shapes_follow_the_data(cuda):
         got = net.blob(k)
         assert got.shape[0] == len(keep)
         assert np.array_equal(got, full[k][: len(keep)]), k
+
+
+def test_partial_forward_may_start_inside_a_fused_group(cuda):
+    """Net::ForwardFromTo(start, end) is part of the mirrored API (net.cpp:544-555).  A range that starts at a layer the
+    fusion pass folded into another one (pool1 lives in conv1_2's epilogue, roi_pool_ctx is pooled by roi_pool_org's
+    launch) is widened back to that layer, and a mark left by a range that ended between the two never leaks into the
+    next call: every such partial forward reproduces the full forward bit for bit."""
+    from mscnn_b200 import models, net as mnet, synth
+    mnet.set_precision("fp32")
+    b, h, w = 2, 96, 320
+    net = mnet.Net(models.kitti(h, w, 8, False, batch=b))
+    net.set_params(synth.make_weights(net.layers()))
+    want = {k: v.copy() for k, v in net.forward(data=synth.make_images(b, h, w)).items()}
+    pool3 = net.blob("pool3")
+    for start in ("pool1", "pool3", "roi_pool_ctx", "roi_pool_org"):
+        net.forward_only(start=start)
+        got = {k: net.blob(k) for k in want}
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (start, k)
+    net.forward_only(end="conv3_3")          # ends between conv3_3 (which pools) and pool3
+    net.forward_only(start="conv4_1")        # must NOT find a stale "already pooled" mark anywhere
+    assert np.array_equal(net.blob("pool3"), pool3)
+    for k in want:
+        assert np.array_equal(net.blob(k), want[k]), k

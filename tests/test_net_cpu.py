@@ -156,6 +156,19 @@ def test_every_shipped_deploy_net_loads():
         assert "data" in net.blob_names
 
 
+def test_fused_groups_are_static():
+    """The fusion pass records who does a folded layer's work: pool1/2/3 -> their convolution, the context ROIPooling ->
+    the object one (the group's leader); everything else does its own.  ForwardFromTo widens a range start to it."""
+    from mscnn_b200 import models
+    from mscnn_b200.net import Net
+    net = Net(models.kitti(96, 320, 8, False, batch=1))
+    assert net.fused_producer("pool1") == "conv1_2" and net.fused_producer("pool2") == "conv2_2"
+    assert net.fused_producer("pool3") == "conv3_3"
+    assert net.fused_producer("pool4") == "pool4"            # reads conv4_3 through a Split top: not folded
+    assert net.fused_producer("roi_pool_ctx") == "roi_pool_org" and net.fused_producer("roi_pool_org") == "roi_pool_org"
+    assert net.fused_producer("conv4_3") == "conv4_3" and net.fused_producer("fc6") == "fc6"
+
+
 def test_params_shared_by_name():
     """ParamSpec names make layers share one blob (Net::AppendParam, net.cpp:448-538): the cascade
     nets' third-stage ensemble heads reuse the first- and second-stage weights."""
