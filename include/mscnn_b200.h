@@ -106,6 +106,9 @@ typedef struct mscnn_conv_desc {
   const int* dyn_n;
 } mscnn_conv_desc;
 MSCNN_API int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream);
+/* Host-only: the launch plan mscnn_conv_forward would use for `d` as one line of text (kernel instantiation, pixel box,
+ * ring layout, CTA pairs, row-share halo, register pooling); no CUDA call, the pointers only have to be non-NULL. */
+MSCNN_API int mscnn_conv_plan_describe(const mscnn_conv_desc* d, char* buf, int cap);
 
 /* Weight packing (done once at load time; replaces nothing in the reference -- Caffe keeps
  * [Cout][Cin][KH][KW] fp32, blob layout base_conv_layer.cpp:135-142).

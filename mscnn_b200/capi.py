@@ -101,6 +101,8 @@ def _declare(L: C.CDLL) -> None:
     L.mscnn_config_reload.argtypes = []
     L.mscnn_conv_forward.restype = c_int
     L.mscnn_conv_forward.argtypes = [C.POINTER(ConvDesc), c_void_p]
+    L.mscnn_conv_plan_describe.restype = c_int
+    L.mscnn_conv_plan_describe.argtypes = [C.POINTER(ConvDesc), C.c_char_p, c_int]
     L.mscnn_pack_conv_weights.restype = c_int
     L.mscnn_pack_conv_weights.argtypes = [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]
     L.mscnn_pack_fc_weights.restype = c_int

@@ -969,7 +969,7 @@ void conv_plan_cache_clear() {
   g_plans.clear();
 }
 
-static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan);
+static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan, bool encode_maps = true);
 
 }  // namespace mscnn
 
@@ -1022,7 +1022,7 @@ extern "C" int mscnn_conv_forward(const mscnn_conv_desc* d, void* stream_v) {
 
 namespace mscnn {
 
-static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan) {
+static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan, bool encode_maps) {
   const Config& cfg = config();
   if (!d->x_hi || !d->w_hi || !d->bias) return MSCNN_ERR_INVALID;
   if (d->C % 64 != 0) return MSCNN_ERR_INVALID;
@@ -1216,8 +1216,14 @@ static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan) {
             d->N, d->H, d->W, d->C, d->Cout_pad, d->KH, d->KW, BN, p.box_w, p.box_h, p.box_n, p.mt, p.fat, p.wide, p.rowshare, p.sa_slots, p.sb_slots, p.vpool, p.a_taps, p.b_split, p.pair, p.num_terms, stages,
             epi_bufs, smem, m_tiles_total / p.mt * p.n_tiles);
 
+  plan->BN = BN;
+  plan->smem = smem;
   CUtensorMap* maps = plan->maps;
   memset(maps, 0, sizeof(plan->maps));
+  if (!encode_maps) {  // mscnn_conv_plan_describe: the shape decisions only, no driver call
+    plan->grid = 0;
+    return MSCNN_OK;
+  }
   const uint32_t obox[4] = {64u, (uint32_t)p.box_w, (uint32_t)p.box_h, (uint32_t)p.box_n};
   const uint32_t abox[4] = {64u, (uint32_t)(p.box_w + (p.a_taps == 3 ? 2 : 0)), (uint32_t)(p.vpool ? 2 : p.box_h), (uint32_t)p.box_n};
   const uint64_t adim[4] = {(uint64_t)d->C, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->N};
@@ -1288,3 +1294,21 @@ static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan) {
 }
 
 }  // namespace mscnn
+
+// The launch plan mscnn_conv_forward would use for `d`, as text, WITHOUT touching the device (no tensor map is encoded,
+// the pointers in `d` only have to be non-NULL where the call would require them): which instantiation, pixel box, ring
+// layout, CTA pairs, row-share halo, register pooling.  Host-side tests pin the variant every full-size layer takes.
+extern "C" int mscnn_conv_plan_describe(const mscnn_conv_desc* d, char* buf, int cap) {
+  if (!d || !buf || cap <= 0) return MSCNN_ERR_INVALID;
+  mscnn::ConvPlan plan;
+  const int rc = mscnn::build_plan(d, &plan, false);
+  if (rc != MSCNN_OK) return rc;
+  const mscnn::IgemmParams& p = plan.p;
+  const int n = snprintf(buf, (size_t)cap,
+                         "kernel=conv_igemm_kernel<%d, %s> box=%dx%dx%d mt=%d terms=%d fat=%d wide=%d rings=%d(%d+%d) a_taps=%d "
+                         "b_split=%d vpool=%d pool=%d acc_sets=%d stages=%d epi_bufs=%d smem=%zu dyn=%d",
+                         plan.BN, p.pair ? "true" : "false", p.box_w, p.box_h, p.box_n, p.mt, p.num_terms, p.fat, p.wide,
+                         p.rowshare, p.sa_slots, p.sb_slots, p.a_taps, p.b_split, p.vpool, p.pool, p.acc_sets, p.stages,
+                         p.epi_bufs, plan.smem, p.dyn_n ? 1 : 0);
+  return (n > 0 && n < cap) ? MSCNN_OK : MSCNN_ERR_INVALID;
+}

@@ -48,6 +48,23 @@ def test_imresize_matches_torch_antialias_bicubic_in_the_interior():
         assert np.abs(a - t)[8:-8, 8:-8].max() < 1e-13
 
 
+def test_imresize_matches_pillow_bicubic_in_the_interior():
+    """A second independent implementation of the same published algorithm: Pillow's BICUBIC resize (a = -0.5, kernel
+    support scaled by the reduction factor when shrinking) on float images agrees with the restatement to float32
+    precision away from the borders, for enlarging, shrinking and mixed size pairs incl. the KITTI one.  (At the borders
+    Pillow renormalises the truncated window where imresize mirrors the image; uint8 images additionally differ by the
+    pass order and the per-pass uint8 rounding, which are covered by the hand-derived cases below.)"""
+    Image = pytest.importorskip("PIL.Image")
+    from oracle import port
+    rng = np.random.default_rng(0)
+    for (h, w), (H, W) in [((37, 53), (80, 120)), ((90, 130), (40, 50)), ((375, 1242), (768, 2560)), ((64, 64), (31, 97))]:
+        img = rng.uniform(0, 255, (h, w)).astype(np.float32)
+        ref = port.imresize(img[:, :, None].astype(np.float64), (H, W))[:, :, 0]
+        pil = np.asarray(Image.fromarray(img, mode="F").resize((W, H), Image.Resampling.BICUBIC), dtype=np.float64)
+        m = 8
+        assert np.abs(ref - pil)[m:-m, m:-m].max() < 1e-4, ((h, w), (H, W))
+
+
 def test_imresize_u8_rounds_and_saturates_per_pass():
     img = np.zeros((8, 8, 3), np.uint8)
     img[:, 4:] = 255                           # a step edge overshoots with a cubic kernel: must clamp to 0..255
