@@ -345,6 +345,11 @@ def main() -> None:
     comm = parallel.Comm() if (use_gather and not use_peer) else None
     per = parallel.payload_floats(B, cap)
     xchg = parallel.PeerExchange(B, cap, generations=args.generations) if use_peer else None
+    exchange_note = None
+    if use_peer and not xchg.ok:       # peer mapping unavailable on this box: every rank falls back to NCCL together
+        exchange_note = f"peer-memory exchange unavailable ({xchg.error}); fell back to --exchange nccl"
+        xchg, use_peer = None, False
+        comm = parallel.Comm()
     payload_all = torch.zeros(per * world, device=dev) if (use_gather and not use_peer) else None
     host_payload = torch.zeros(per).pin_memory() if use_gather else None
     cur_stream = torch.cuda.current_stream().cuda_stream
@@ -590,6 +595,7 @@ def main() -> None:
         "gpu_launches": r["launched"],
         "roofline": roofline(r, pk),
         "clocks": r["clocks"],
+        "exchange": ("off" if not use_gather else "peer" if use_peer else "nccl") + (f" ({exchange_note})" if exchange_note else ""),
         "per_rank_step_ms": r["per_rank"],
         "top_layers_ms": [[k, round(v, 3)] for v, k in r["top"]],
         "layers_ms": r["layers"],

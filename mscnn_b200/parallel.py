@@ -137,19 +137,40 @@ class PeerExchange:
         self.world = dist.get_world_size() if world is None else world
         self.batch, self.cap = batch, cap
         self.per = payload_floats(batch, cap)
+        # Every rank walks through the same collective calls whatever happens locally, and the outcome is agreed on
+        # (`self.ok`): a box where peer mapping is unavailable makes ALL ranks fall back together (bench.py: NCCL).
+        self._h = None
+        self.ok, self.error = True, ""
         h = C.c_void_p()
-        capi.check(self._L.mscnn_xchg_create(C.byref(h), self.world, self.rank, self.per, generations), "xchg_create")
-        self._h = h
+        handle = None
+        try:
+            capi.check(self._L.mscnn_xchg_create(C.byref(h), self.world, self.rank, self.per, generations), "xchg_create")
+            self._h = h
+            if self.world > 1:
+                buf = C.create_string_buffer(XCHG_HANDLE_BYTES)
+                capi.check(self._L.mscnn_xchg_ipc_handle(self._h, buf), "xchg_ipc_handle")
+                handle = bytes(buf.raw)
+        except capi.MscnnError as e:
+            self.ok, self.error = False, str(e)
         if self.world > 1:
-            buf = C.create_string_buffer(XCHG_HANDLE_BYTES)
-            capi.check(self._L.mscnn_xchg_ipc_handle(self._h, buf), "xchg_ipc_handle")
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(buf.raw))
-            for p, hb in enumerate(handles):
-                if p != self.rank:
-                    capi.check(self._L.mscnn_xchg_open_peer_ipc(self._h, p, C.create_string_buffer(hb, XCHG_HANDLE_BYTES)),
-                               f"xchg_open_peer_ipc({p})")
-            dist.barrier()          # every rank has mapped every buffer before anybody pushes
+            dist.all_gather_object(handles, handle)
+            if self.ok and all(hb is not None for hb in handles):
+                try:
+                    for p, hb in enumerate(handles):
+                        if p != self.rank:
+                            capi.check(self._L.mscnn_xchg_open_peer_ipc(self._h, p, C.create_string_buffer(hb, XCHG_HANDLE_BYTES)),
+                                       f"xchg_open_peer_ipc({p})")
+                except capi.MscnnError as e:
+                    self.ok, self.error = False, str(e)
+            else:
+                self.ok = False
+            verdicts = [None] * self.world
+            dist.all_gather_object(verdicts, (self.ok, self.error))   # also the barrier: every buffer is mapped before any push
+            self.ok = all(v[0] for v in verdicts)
+            self.error = "; ".join(f"rank {r}: {v[1]}" for r, v in enumerate(verdicts) if v[1])
+        if not self.ok:
+            self.close()
 
     @property
     def handle(self) -> C.c_void_p:

@@ -105,6 +105,34 @@ cases.append(dict(
                "net pixels; :110-111 tx, tw divided by ratios(2) = 4 -> 100, 100; ty, th by ratios(1) = 2 -> 50, 100.  "
                "Clip against orgW = 640, orgH = 384: unchanged.  prob = 1/5."))
 
+# --------------------------------------------------- cascade driver (examples/kitti_car/run_cascademscnn.m:96-123)
+cases.append(dict(
+    name="cascade_rescale_clip_plus_one",
+    kind="cascade", cls_id=2, net_hw=[768, 2560], ratios=[2.0, 4.0], org_hw=[384, 640],
+    proposals=[[0, 40, 20, 440, 220], [0, 100, 100, 99, 300], [0, 7, 7, 7, 8]],
+    cls_prob=[[0.1, 0.9], [0.2, 0.8], [0.3, 0.7]],
+    output_bbox=[[0, 400, 100, 800, 300], [0, -8, 700, 2700, 900], [0, 4, 4, 8, 8]],
+    dets=[[100.0, 50.0, 101.0, 101.0, 0.9], [1.0, 2.0, 2.0, 3.0, 0.7]],
+    tol=2e-6,
+    derivation="run_cascademscnn.m:97-103 on output_bbox [x1 y1 x2 y2]: x / ratios(2) = 4, y / ratios(1) = 2, then "
+               "[x1 y1] = max(0, .), x2 = min(x2, orgW = 640), y2 = min(y2, orgH = 384), [w h] = [x2 y2] - [x1 y1] + 1.  Row 1: "
+               "[100 50 200 150] -> w = h = 101, prob 0.9.  Row 2: its PROPOSAL has w = 99 - 100 + 1 = 0 under the '+ 1' "
+               "convention of :110 -> dropped at :113 (keep_id = proposals(:,3) ~= 0 & proposals(:,4) ~= 0) although its "
+               "output box [-8 700 2700 900] would clip to a valid [0 350 640 384].  Row 3: proposal [7 7 7 8] has w = 1, "
+               "h = 2 (kept); box [4 4 8 8] -> [1 2 2 4] -> w = 2, h = 3, prob 0.7.  bbNms 'maxg' 0.5: rows 1 and 3 are "
+               "disjoint.  Output by descending prob."))
+cases.append(dict(
+    name="cascade_nms_uses_plus_one_extents",
+    kind="cascade", cls_id=2, net_hw=[100, 100], ratios=[1.0, 1.0], org_hw=[100, 100],
+    proposals=[[0, 0, 0, 9, 9], [0, 0, 0, 9, 9]],
+    cls_prob=[[0.4, 0.6], [0.5, 0.5]],
+    output_bbox=[[0, 0, 0, 9, 9], [0, 0, 0, 9, 4]],
+    dets=[[0.0, 0.0, 10.0, 10.0, 0.6], [0.0, 0.0, 10.0, 5.0, 0.5]],
+    tol=2e-6,
+    derivation="With the + 1 of :103 the boxes are [0 0 10 10] and [0 0 10 5]: overlap 50 / (100 + 50 - 50) = 0.5 exactly, "
+               "not > 0.5 -> both kept (without the + 1 it would be 9*4 / (81 + 36 - 36) = 0.444, also kept, but "
+               "the extents reported would be 9 and 4: the expected rows pin the convention)."))
+
 out = Path(__file__).resolve().parent / "a15_postprocess_cases.json"
 out.write_text(json.dumps(dict(source="hand-derived from run_mscnn_detection.m:75-120 and bbNms.m:75-126; see make_a15_vectors.py",
                                cases=cases), indent=1))

@@ -2,7 +2,9 @@
 (tests/golden/a15_postprocess_cases.json, written by tests/golden/make_a15_vectors.py with the derivation of every number
 from /root/reference/examples/kitti_car/run_mscnn_detection.m:75-120 and /root/reference/utils/bbNms.m:75-126): greedy
 'maxg' order, overlap exactly 0.5 (strict >), score ties (stable sort), boxes of negative width produced by the border
-clipping, zero-extent / low-score proposals dropped at :82, the '>=' at the threshold, delta decode, softmax, ratios.
+clipping, zero-extent / low-score proposals dropped at :82, the '>=' at the threshold, delta decode, softmax, ratios; and
+the cascade driver's variant (/root/reference/examples/kitti_car/run_cascademscnn.m:96-123: rescale, clip, the "+ 1"
+extent convention, proposals of zero extent dropped at :113).
 CPU: the restatement (oracle/port.py, oracle/mscnn_oracle.c).  GPU: the device kernels through the C ABI."""
 import json
 from pathlib import Path
@@ -27,6 +29,42 @@ def test_postprocess_hand_vectors_oracle(case):
                                   np.array(case["bbox_pred"], np.float32), cls_id=case["cls_id"],
                                   ratios=tuple(case["ratios"]), net_hw=tuple(case["net_hw"]),
                                   org_hw=tuple(case["org_hw"]) if "org_hw" in case else None)
+    want = np.array(case["dets"], dtype=np.float64)
+    assert got.shape == want.shape, (got, case["derivation"])
+    np.testing.assert_allclose(got, want, rtol=case["tol"], atol=case["tol"], err_msg=case["derivation"])
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c["kind"] == "cascade"], ids=lambda c: c["name"])
+def test_cascade_postprocess_hand_vectors_oracle(case):
+    from oracle import port
+    got = port.cascade_detect_postprocess(np.array(case["proposals"], np.float32), np.array(case["cls_prob"], np.float32),
+                                          np.array(case["output_bbox"], np.float32), cls_id=case["cls_id"],
+                                          ratios=tuple(case["ratios"]), org_hw=tuple(case["org_hw"]),
+                                          net_hw=tuple(case["net_hw"]))
+    want = np.array(case["dets"], dtype=np.float64)
+    assert got.shape == want.shape, (got, case["derivation"])
+    np.testing.assert_allclose(got, want, rtol=case["tol"], atol=case["tol"], err_msg=case["derivation"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in CASES if c["kind"] == "cascade"], ids=lambda c: c["name"])
+def test_cascade_postprocess_hand_vectors_device(cuda, case):
+    import torch
+    from mscnn_b200 import capi, ops
+    prop = np.array(case["proposals"], np.float32)
+    cfg = capi.DetectCfg()
+    cfg.num_cls, cfg.cls_id = 2, case["cls_id"]
+    cfg.nms_overlap = 0.5
+    cfg.ratio_h, cfg.ratio_w = case["ratios"]
+    cfg.org_h, cfg.org_w = case["org_hw"]
+    cfg.max_rois_per_image = 64
+    n = len(prop)
+    num_out = torch.tensor([n, n, n], dtype=torch.int32, device=cuda)
+    dets, cnt = ops.cascade_detect_postprocess(cfg, 1, torch.from_numpy(prop).to(cuda),
+                                               torch.from_numpy(np.array(case["cls_prob"], np.float32)).to(cuda),
+                                               torch.from_numpy(np.array(case["output_bbox"], np.float32)).to(cuda), num_out)
+    torch.cuda.synchronize()
+    got = dets[0, :int(cnt[0].item())].cpu().numpy()
     want = np.array(case["dets"], dtype=np.float64)
     assert got.shape == want.shape, (got, case["derivation"])
     np.testing.assert_allclose(got, want, rtol=case["tol"], atol=case["tol"], err_msg=case["derivation"])
