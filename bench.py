@@ -218,11 +218,16 @@ def run_reference(args) -> None:
         print(json.dumps({**base, "unavailable": "oracle/_ref/libmscnn_ref.so was not built (needs /root/reference at build time)"}))
         return
     cores = ref.set_blas_threads(ncpu)
-    small = _ref_net(CPU_SAMPLE_H, CPU_SAMPLE_W)
+    # tests/test_bench_cpu.py shrinks the image to exercise this arm in seconds; the line then says so in `config`
+    full_h, full_w = NET_H, NET_W
+    if os.environ.get("MSCNN_BENCH_TEST_HW"):
+        full_h, full_w = (int(v) for v in os.environ["MSCNN_BENCH_TEST_HW"].split("x"))
+        base["config"]["workload"] = f"TEST OVERRIDE {full_h}x{full_w} (not the benchmark workload)"
+    small = _ref_net(min(CPU_SAMPLE_H, full_h), min(CPU_SAMPLE_W, full_w))
     for _ in range(max(1, min(args.warmup, 2))):
         small.forward()
     del small
-    net = _ref_net(NET_H, NET_W)
+    net = _ref_net(full_h, full_w)
     names = net.layer_names
     passes = _chunks(len(names), max(1, args.steps))
     step_s = []
@@ -236,7 +241,7 @@ def run_reference(args) -> None:
     n_full = len(passes)
     value = n_full / total
     rows = int(net.blob_shape("proposals")[0])
-    sample = (f"{n_full} complete forward(s) of 1 synthetic 3x{NET_H}x{NET_W} image through the full mscnn-8s net (R = {rows} "
+    sample = (f"{n_full} complete forward(s) of 1 synthetic 3x{full_h}x{full_w} image through the full mscnn-8s net (R = {rows} "
               f"proposals), cut into {len(step_s)} consecutive layer-range steps; Caffe CPU mode, reference layers compiled "
               f"verbatim, {ref.blas_backend()}, {cores} BLAS threads of {ncpu} host cpus; images/s = {n_full} / {total:.1f} s")
     line = {**base, "value": value, "ms_per_step": total / len(step_s) * 1e3,
