@@ -118,8 +118,9 @@ POOLED = ("conv1_2", "conv2_2", "conv3_3")     # 2x2 max pooling fused into the 
 def kernel_groups(net, layer_ms: dict, split: bool) -> list[dict]:
     """Per kernel instantiation: the Convolution / InnerProduct layers it serves in this net, their summed device
     time (CUDA events per layer) and algorithmic FLOPs.  The instantiation follows from the layer shape exactly as
-    mscnn_conv_forward picks it (conv_igemm.cu pick_block_n / build_plan): BLOCK_N = 256 | 128 | 64 | 32 by padded
-    Cout; CTA pairs for un-pooled BLOCK_N = 256 layers of the fp32-faithful path; conv1_1 has its own kernel."""
+    mscnn_conv_forward picks it (conv_igemm.cu pick_block_n / build_plan; pinned by tests/test_conv_plan_cpu.py):
+    BLOCK_N = 256 | 128 | 64 | 32 by padded Cout; CTA pairs for the BLOCK_N = 256 layers of the fp32-faithful path;
+    conv1_1 has its own kernel."""
     groups: dict[str, dict] = {}
     for name, ltype, shapes in net.layers():
         if ltype not in ("Convolution", "InnerProduct"):
@@ -139,7 +140,7 @@ def kernel_groups(net, layer_ms: dict, split: bool) -> list[dict]:
         else:
             cpad = (co + 63) // 64 * 64
             bn = 256 if cpad % 256 == 0 else 128 if cpad % 128 == 0 else 64
-            pair = split and bn == 256 and name not in POOLED and cpad >= 64 and co > 32
+            pair = split and bn == 256 and co > 32      # un-pooled and pooled (conv3_3) BLOCK_N = 256 layers alike
             kern, bound = f"conv_igemm_kernel<{bn}, {'true' if pair else 'false'}>", "tensor"
         g = groups.setdefault(kern, {"kernel": kern, "bound": bound, "layers": [], "ms": 0.0, "gflop": 0.0})
         g["layers"].append(name)

@@ -23,6 +23,7 @@ static void load_locked() {
   c.no_vpool = on("MSCNN_NO_VPOOL");
   c.no_ring256 = on("MSCNN_NO_RING256");
   c.no_2cta = on("MSCNN_NO_2CTA");
+  c.no_2cta_pool = on("MSCNN_NO_2CTA_POOL");
   c.no_bf16_rings = on("MSCNN_NO_BF16_RINGS");
   c.no_head_taps = on("MSCNN_NO_HEAD_TAPS");
   c.no_fusion = on("MSCNN_NO_FUSION");

@@ -1181,7 +1181,8 @@ static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan, bool encode_maps
     const int a_plane = halo ? ((p.box_w + 2) * 128 + 1023) / 1024 * 1024 : kABytes;
     // CTA pairs (MSCNN_NO_2CTA=1 turns them off): half weight tiles per CTA, MMAs of M = 256 issued by the leader;
     // conv3_2 2.13 -> 2.00 ms, the step 37.3 -> 35.5 ms on the same B200 (profiles/r01n_summary.md)
-    p.pair = (!cfg.no_2cta && d->out_mode == MSCNN_OUT_NHWC_BF16 && !pool && mscnn_sm_count() >= 2) ? 1 : 0;
+    // (pooled layers too: the 2x2 pooling of the staged tile is per CTA and does not care who issued the MMAs)
+    p.pair = (!cfg.no_2cta && !cfg.no_2cta_pool_check(pool) && d->out_mode == MSCNN_OUT_NHWC_BF16 && mscnn_sm_count() >= 2) ? 1 : 0;
     const int a_slot = 2 * a_plane, b_slot = p.pair ? b_bytes / 2 : b_bytes;
     const int eb = (epi_unit == 0) ? 0 : 1;
     const int rings = budget - misc - eb * epi_unit;

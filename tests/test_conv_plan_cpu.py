@@ -60,8 +60,9 @@ def test_full_size_trunk_variants():
     for name in ("conv3_1", "conv3_2"):
         assert p[name]["kernel"] == "conv_igemm_kernel<256, true>", p[name]
         assert p[name]["box"] == "128x1x1" and p[name]["a_taps"] == "3" and p[name]["b_split"] == "1" and p[name]["mt"] == "1"
-    # the pooled conv3_3 stays on single CTAs (pooling in the epilogue needs both rows of a 2x2 window in one CTA tile)
-    assert p["conv3_3"]["kernel"] == "conv_igemm_kernel<256, false>" and p["conv3_3"]["pool"] == "1" and p["conv3_3"]["b_split"] == "1"
+    # the pooled conv3_3: even-sized 2-D boxes (a 2x2 window never straddles tiles), pooled in the epilogue per CTA, pairs too
+    assert p["conv3_3"]["kernel"] == "conv_igemm_kernel<256, true>" and p["conv3_3"]["pool"] == "1" and p["conv3_3"]["b_split"] == "1"
+    assert p["conv3_3"]["box"] == "64x2x1" and p["conv3_3"]["a_taps"] == "1"
     # 2-D boxes further down (W = 320 / 160 / 80): pairs without the halo
     for name in ("conv4_1", "conv4_2", "conv5_1", "conv6_1"):
         assert p[name]["kernel"] == "conv_igemm_kernel<256, true>" and p[name]["a_taps"] == "1" and p[name]["b_split"] == "1", p[name]
@@ -106,5 +107,5 @@ def test_bench_roofline_grouping_names_the_same_kernels():
         lib = _describe(n, cin, h, w, cout, 3, 1, pooled=pool)["kernel"]
         cpad = (cout + 63) // 64 * 64
         bn = 256 if cpad % 256 == 0 else 128 if cpad % 128 == 0 else 64
-        pair = bn == 256 and name not in bench.POOLED
+        pair = bn == 256
         assert lib == f"conv_igemm_kernel<{bn}, {'true' if pair else 'false'}>", (name, lib)
