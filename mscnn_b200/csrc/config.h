@@ -10,7 +10,6 @@ struct Config {
   bool no_head_taps, no_fusion, no_pool_fusion, no_roi_fuse, no_graph;
   bool verbose_conv, c3_swap;
   bool no_2cta_pool;  // MSCNN_NO_2CTA_POOL: keep the pooled BLOCK_N = 256 layers (conv3_3) on single CTAs
-  bool no_2cta_pool_check(bool pool) const { return pool && no_2cta_pool; }
   int mt;          // MSCNN_MT, 0 = per-layer default
   int conv1_mode;  // MSCNN_CONV1: 0 = tensor-core kernel (default), 1 = pair, 2 = direct, 3 = patch
   unsigned epoch;  // bumped by every reload: cached plans carry the epoch they were built under

@@ -1182,7 +1182,7 @@ static int build_plan(const mscnn_conv_desc* d, ConvPlan* plan, bool encode_maps
     // CTA pairs (MSCNN_NO_2CTA=1 turns them off): half weight tiles per CTA, MMAs of M = 256 issued by the leader;
     // conv3_2 2.13 -> 2.00 ms, the step 37.3 -> 35.5 ms on the same B200 (profiles/r01n_summary.md)
     // (pooled layers too: the 2x2 pooling of the staged tile is per CTA and does not care who issued the MMAs)
-    p.pair = (!cfg.no_2cta && !cfg.no_2cta_pool_check(pool) && d->out_mode == MSCNN_OUT_NHWC_BF16 && mscnn_sm_count() >= 2) ? 1 : 0;
+    p.pair = (!cfg.no_2cta && !(pool && cfg.no_2cta_pool) && d->out_mode == MSCNN_OUT_NHWC_BF16 && mscnn_sm_count() >= 2) ? 1 : 0;
     // pooled + an odd number of M tiles (a phantom tile in the last pair): that combination has not been run on the
     // device yet, so it keeps the validated single-CTA build (batch-1 toy sizes only; every BASELINE size is even)
     if (pool && (m_tiles_total & 1)) p.pair = 0;
