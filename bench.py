@@ -8,14 +8,18 @@ KITTI-car forward, batch 8 per B200, 3x768x2560 synthetic input; proposals/sec r
 
 A "step" = one forward of one batch of 8 images per GPU through the whole path: conv trunk,
 proposal heads, BoxOutput (decode + top-2000 + NMS), ROI pooling, detection head, final-detection
-post-process; for N > 1 followed by one NCCL all-gather of the final boxes.
+post-process; for N > 1 the post-process kernel also pushes the packed final detections into every rank's
+gather buffer over NVLink (--exchange peer, default) or one ncclAllGather follows (--exchange nccl).
 
   value  : images/s, whole job, inputs already resident in HBM (fp32-faithful split-bf16 path, the
            path that meets the 1e-3 parity gate); `bf16` carries the same measurement for the plain
            bf16 tensor-core path (config 3 of BASELINE.json asks for both).
   e2e    : same metric through the public API (mscnn_b200.net.Net) with HOST buffers: pinned-host
            -> device copy of the batch and device -> host copy of the detections inside every step.
-  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md section "Measurement".
+  roofline : the DOMINANT kernel instantiation (live CUDA-event times of the layers it serves); every instantiation in
+           roofline.by_kernel; traffic from the committed ncu launch list of the current build.
+  cpu_baseline / --impl reference : the reference's own CPU layers (oracle/_ref) on the SAME configuration, BLAS pinned to
+           every host thread.  clocks / gpu_launches / per_rank_step_ms: see DESIGN.md section "Measurement".
 """
 from __future__ import annotations
 
