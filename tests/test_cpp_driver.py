@@ -48,6 +48,22 @@ def test_cpp_host_compiles_links_and_builds_the_net(tmp_path):
     assert any(l.startswith("registry:") and "HostPass=1 BoxOutput=1" in l for l in lines)
 
 
+def test_multi_gpu_driver_compiles_and_links_without_a_gpu(tmp_path):
+    """examples/multi_gpu_driver.cpp (one host thread per GPU, C ABI only: net facade, peer-memory exchange, NCCL
+    communicator) builds with plain g++ against include/mscnn_b200.h and links against the library; without a device
+    it stops with its usage / device-count message instead of crashing."""
+    from mscnn_b200 import capi
+    capi.lib()
+    exe = tmp_path / "multi_gpu_driver"
+    cmd = ["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), "-I", "/usr/local/cuda/include",
+           str(ROOT / "examples/multi_gpu_driver.cpp"), "-L", str(ROOT / "mscnn_b200"), "-lmscnn_b200",
+           "-L", "/usr/local/cuda/lib64", "-lcudart", "-lpthread", f"-Wl,-rpath,{ROOT / 'mscnn_b200'}", "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 2 and "usage:" in r.stderr
+
+
 @pytest.mark.gpu
 def test_cpp_host_forward_matches_the_facade(cuda, tmp_path):
     from mscnn_b200 import models, net as mnet
