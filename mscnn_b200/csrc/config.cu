@@ -26,10 +26,6 @@ static void load_locked() {
   c.no_2cta_pool = on("MSCNN_NO_2CTA_POOL");
   c.no_bf16_rings = on("MSCNN_NO_BF16_RINGS");
   c.no_head_taps = on("MSCNN_NO_HEAD_TAPS");
-  c.no_fusion = on("MSCNN_NO_FUSION");
-  c.no_pool_fusion = on("MSCNN_NO_POOL_FUSION");
-  c.no_roi_fuse = on("MSCNN_NO_ROI_FUSE");
-  c.no_graph = on("MSCNN_NO_GRAPH");
   c.verbose_conv = on("MSCNN_VERBOSE_CONV");
   c.c3_swap = on("MSCNN_C3_SWAP");
   if (const char* e = std::getenv("MSCNN_MT")) c.mt = atoi(e);

@@ -7,7 +7,7 @@ namespace mscnn {
 
 struct Config {
   bool no_fat, no_wide, no_rowshare, no_vpool, no_ring256, no_2cta, no_bf16_rings;
-  bool no_head_taps, no_fusion, no_pool_fusion, no_roi_fuse, no_graph;
+  bool no_head_taps;
   bool verbose_conv, c3_swap;
   bool no_2cta_pool;  // MSCNN_NO_2CTA_POOL: keep the pooled BLOCK_N = 256 layers (conv3_3) on single CTAs
   int mt;          // MSCNN_MT, 0 = per-layer default
